@@ -1,0 +1,497 @@
+// filtlong_b200/csrc/fl_api.cu -- context management, host packer, batch entry points, result
+// download and the deterministic synthetic-workload generators behind the C ABI.
+#include <cmath>
+
+#include "fl_internal.cuh"
+
+static std::string g_create_error;
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" const char *fl_version(void) { return "filtlong-b200 0.1 (Filtlong v0.3.1 semantics, sm_100a)"; }
+
+extern "C" const char *fl_last_error(const fl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+static int validate_params(const fl_params *p, std::string &why) {
+    if (!p) { why = "params is NULL"; return FL_EINVAL; }
+    if (p->window_size <= 0) { why = "the value for --window_size must be a positive integer"; return FL_EINVAL; }   // arguments.cpp:388-392
+    if (p->split_set && p->split <= 0) { why = "the value for --split must be a positive integer"; return FL_EINVAL; }   // arguments.cpp:381-385
+    if (p->length_weight < 0.0 || p->mean_q_weight < 0.0 || p->window_q_weight < 0.0) {
+        why = "weight values cannot be negative";                                                                      // arguments.cpp:374-378
+        return FL_EINVAL;
+    }
+    return FL_OK;
+}
+
+extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) {
+    if (!out) return FL_EINVAL;
+    *out = nullptr;
+    std::string why;
+    if (validate_params(params, why) != FL_OK) { g_create_error = why; return FL_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+        return FL_ENODEV;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return FL_ECUDA; }
+    fl_ctx *c = new (std::nothrow) fl_ctx();
+    if (!c) return FL_ENOMEM;
+    c->device = device;
+    c->p = *params;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_scalars, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_scalars, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMallocHost(&c->h_scalars, 64 * sizeof(unsigned long long))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return FL_ECUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return FL_OK;
+}
+
+extern "C" void fl_ctx_destroy(fl_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->d_bitmap) cudaFree(c->d_bitmap);
+    for (int i = 0; i < 4; ++i) if (c->d_seen[i]) cudaFree(c->d_seen[i]);
+    if (c->d_tfirst) cudaFree(c->d_tfirst);
+    if (c->d_bittime) cudaFree(c->d_bittime);
+    if (c->d_lut) cudaFree(c->d_lut);
+    if (c->d_buckets) cudaFree(c->d_buckets);
+    if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    fl_norm_select_free(c);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" int fl_ctx_set_stream(fl_ctx *c, void *cuda_stream) {
+    if (!c) return FL_EINVAL;
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return FL_OK;
+}
+
+extern "C" int fl_ctx_sync(fl_ctx *c) {
+    if (!c) return FL_EINVAL;
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FL_OK;
+}
+
+extern "C" int fl_ctx_set_params(fl_ctx *c, const fl_params *p) {
+    if (!c) return FL_EINVAL;
+    std::string why;
+    if (validate_params(p, why) != FL_OK) { c->set_error(why); return FL_EINVAL; }
+    c->p = *p;
+    return FL_OK;
+}
+
+extern "C" uint64_t fl_ctx_launch_count(const fl_ctx *c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// host packer
+// ---------------------------------------------------------------------------------------------
+extern "C" uint64_t fl_padded_len(int64_t len) {
+    if (len <= 0) return 0;
+    return ((uint64_t)len + FL_ALIGN_BASES - 1) & ~(uint64_t)(FL_ALIGN_BASES - 1);
+}
+
+extern "C" void fl_pack_sequence(const char *seq, const char *qual, int64_t len, uint64_t off, uint32_t *seq2b,
+                                 uint8_t *qual_out, uint32_t *nmask) {
+    if (qual_out && qual) memcpy(qual_out + off, qual, (size_t)len);
+    if (!seq2b && !nmask) return;
+    for (int64_t i = 0; i < len; ++i) {
+        uint32_t code = 0, other = 0;
+        switch (seq[i]) {                         // kmers.cpp:176-196
+            case 'A': case 'a': code = 0; break;
+            case 'C': case 'c': code = 1; break;
+            case 'G': case 'g': code = 2; break;
+            case 'T': case 't': code = 3; break;
+            default: other = 1; break;
+        }
+        const uint64_t b = off + (uint64_t)i;
+        if (seq2b && code) seq2b[b >> 4] |= code << (30 - 2 * (b & 15));
+        if (nmask && other) nmask[b >> 5] |= 1u << (b & 31);
+    }
+}
+
+extern "C" void fl_phred_luts(int32_t window_size, double *q256, double *a256) {
+    for (int b = 0; b < 256; ++b) {
+        int q = (int)(signed char)b - 33;                       // read.cpp:271 (char is signed)
+        double v = 1.0 - pow(10.0, -q / 10.0);                  // read.cpp:272, host libm
+        if (q256) q256[b] = v;
+        if (a256) a256[b] = v / (double)window_size;            // read.cpp:229-230: qualities[i] / window_size
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batches
+// ---------------------------------------------------------------------------------------------
+static int check_batch(fl_ctx *c, const fl_batch *b) {
+    if (!b) { c->set_error("batch is NULL"); return FL_EINVAL; }
+    if (b->n && (!b->off || !b->len)) { c->set_error("batch.off / batch.len missing"); return FL_EINVAL; }
+    if (b->padded_bases % FL_ALIGN_BASES) { c->set_error("batch.padded_bases must be a multiple of 64"); return FL_EINVAL; }
+    return FL_OK;
+}
+
+static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool want_seq, bool want_qual, bool want_nmask) {
+    cudaStream_t s = c->stream;
+    const size_t n = h->n;
+    FL_CUDA(c, c->st_off.reserve(n, 0, s));
+    FL_CUDA(c, c->st_len.reserve(n, 0, s));
+    FL_CUDA(c, cudaMemcpyAsync(c->st_off.p, h->off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    FL_CUDA(c, cudaMemcpyAsync(c->st_len.p, h->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    v->n = h->n;
+    v->padded_bases = h->padded_bases;
+    v->off = c->st_off.p;
+    v->len = c->st_len.p;
+    v->seq2b = nullptr; v->qual = nullptr; v->nmask = nullptr;
+    if (want_seq && h->seq2b) {
+        size_t words = (size_t)(h->padded_bases >> 4);
+        FL_CUDA(c, c->st_seq.reserve(words + 4, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(c->st_seq.p, h->seq2b, words * 4, cudaMemcpyHostToDevice, s));
+        v->seq2b = c->st_seq.p;
+    }
+    if (want_qual && h->qual) {
+        FL_CUDA(c, c->st_qual.reserve((size_t)h->padded_bases + 64, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(c->st_qual.p, h->qual, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
+        v->qual = c->st_qual.p;
+    }
+    if (want_nmask && h->nmask) {
+        size_t words = (size_t)(h->padded_bases >> 5);
+        FL_CUDA(c, c->st_nmask.reserve(words + 4, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(c->st_nmask.p, h->nmask, words * 4, cudaMemcpyHostToDevice, s));
+        v->nmask = c->st_nmask.p;
+    }
+    return FL_OK;
+}
+
+static BatchView view_of_device_batch(const fl_batch *b) {
+    BatchView v{};
+    v.n = b->n; v.padded_bases = b->padded_bases; v.off = b->off; v.len = b->len;
+    v.seq2b = b->seq2b; v.qual = b->qual; v.nmask = b->nmask;
+    return v;
+}
+
+extern "C" int fl_kmers_add_batch(fl_ctx *c, const fl_batch *h, int multi) {
+    if (!c) return FL_EINVAL;
+    FL_TRY(check_batch(c, h));
+    if (h->n == 0) return FL_OK;
+    BatchView v{};
+    FL_TRY(stage_host_batch(c, h, &v, true, false, true));
+    FL_TRY(fl_kmers_add_view(c, v, multi));
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));   // staging buffers are reused by the next call
+    return FL_OK;
+}
+
+extern "C" int fl_kmers_add_batch_device(fl_ctx *c, const fl_batch *d, int multi) {
+    if (!c) return FL_EINVAL;
+    FL_TRY(check_batch(c, d));
+    return fl_kmers_add_view(c, view_of_device_batch(d), multi);
+}
+
+__global__ void k_sum_len(const int32_t *len, uint32_t n, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += (unsigned long long)len[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+#define FL_SCALAR_TOTAL_BASES 16   // slot in d_scalars accumulating the lengths of device batches
+
+extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
+    if (!c) return FL_EINVAL;
+    FL_TRY(check_batch(c, h));
+    if (h->n == 0) return FL_OK;
+    if (c->kmers_count_stale || c->multi_pending) FL_TRY(fl_kmers_recount(c));
+    const bool kmer_mode = c->n_kmers > 0;
+    BatchView v{};
+    FL_TRY(stage_host_batch(c, h, &v, kmer_mode, !kmer_mode, false));
+    FL_TRY(fl_score_view(c, v));
+    for (uint32_t i = 0; i < h->n; ++i) c->total_bases += h->len[i];     // main.cpp:89
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));   // staging buffers are reused by the next call
+    return FL_OK;
+}
+
+extern "C" int fl_reads_push_device(fl_ctx *c, const fl_batch *d) {
+    if (!c) return FL_EINVAL;
+    FL_TRY(check_batch(c, d));
+    if (d->n == 0) return FL_OK;
+    FL_TRY(fl_score_view(c, view_of_device_batch(d)));
+    k_sum_len<<<c->sm_count, 256, 0, c->stream>>>(d->len, d->n, c->d_scalars + FL_SCALAR_TOTAL_BASES);
+    c->launches++;
+    FL_CUDA(c, cudaGetLastError());
+    return FL_OK;
+}
+
+extern "C" int fl_reads_reset(fl_ctx *c) {
+    if (!c) return FL_EINVAL;
+    FL_CUDA(c, cudaMemsetAsync(c->d_scalars + FL_SCALAR_TOTAL_BASES, 0, sizeof(unsigned long long), c->stream));
+    c->n_reads = 0;
+    c->n_rows = 0;
+    c->total_bases = 0;
+    c->finalized = false;
+    return FL_OK;
+}
+
+static int device_total_bases(fl_ctx *c, int64_t *out) {
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 32, c->d_scalars + FL_SCALAR_TOTAL_BASES, sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = c->total_bases + (int64_t)c->h_scalars[32];
+    return FL_OK;
+}
+
+extern "C" int fl_reads_count(fl_ctx *c, uint64_t *n_reads, uint64_t *n_rows, int64_t *total_bases) {
+    if (!c) return FL_EINVAL;
+    if (n_reads) *n_reads = c->n_reads;
+    if (n_rows) *n_rows = c->n_rows;
+    if (total_bases) FL_TRY(device_total_bases(c, total_bases));
+    return FL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int dl(fl_ctx *c, T *host, const T *dev, size_t n) {
+    if (!host || !n) return FL_OK;
+    FL_CUDA(c, cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return FL_OK;
+}
+
+static double host_length_score(int length) {              // read.cpp:241-244
+    double half = 5000.0;
+    return 100.0 * (1.0 + (-half / (length + half)));
+}
+
+extern "C" int fl_results_reads(fl_ctx *c, const fl_read_results *o) {
+    if (!c || !o) return FL_EINVAL;
+    const size_t n = c->n_reads;
+    std::vector<int32_t> len_tmp;
+    int32_t *len_host = o->length;
+    if (o->length_score && !len_host) { len_tmp.resize(n); len_host = len_tmp.data(); }
+    FL_TRY(dl(c, len_host, c->r_len.p, n));
+    FL_TRY(dl(c, o->mean_q, c->r_mean.p, n));
+    FL_TRY(dl(c, o->window_q, c->r_window.p, n));
+    FL_TRY(dl(c, o->passed, c->r_passed.p, n));
+    FL_TRY(dl(c, o->first_base_in_kmer, c->r_first.p, n));
+    FL_TRY(dl(c, o->last_base_in_kmer, c->r_last.p, n));
+    FL_TRY(dl(c, o->n_bad, c->r_nbad.p, n));
+    FL_TRY(dl(c, o->n_child, c->r_nchild.p, n));
+    FL_TRY(dl(c, reinterpret_cast<unsigned long long *>(o->row_start), c->r_rowstart.p, n));
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (o->length_score)
+        for (size_t i = 0; i < n; ++i) o->length_score[i] = host_length_score(len_host[i]);
+    return FL_OK;
+}
+
+extern "C" int fl_results_rows(fl_ctx *c, const fl_row_results *o) {
+    if (!c || !o) return FL_EINVAL;
+    const size_t n = c->n_rows;
+    std::vector<int32_t> s_tmp, e_tmp;
+    int32_t *s_host = o->start, *e_host = o->end;
+    if (o->length_score) {
+        if (!s_host) { s_tmp.resize(n); s_host = s_tmp.data(); }
+        if (!e_host) { e_tmp.resize(n); e_host = e_tmp.data(); }
+    }
+    FL_TRY(dl(c, o->parent, c->w_parent.p, n));
+    FL_TRY(dl(c, s_host, c->w_start.p, n));
+    FL_TRY(dl(c, e_host, c->w_end.p, n));
+    FL_TRY(dl(c, o->mean_q, c->w_mean.p, n));
+    FL_TRY(dl(c, o->window_q, c->w_window.p, n));
+    FL_TRY(dl(c, o->passed, c->w_passed.p, n));
+    if (c->finalized) {
+        FL_TRY(dl(c, o->norm_mean, c->w_nmean.p, n));
+        FL_TRY(dl(c, o->norm_window, c->w_nwindow.p, n));
+        FL_TRY(dl(c, o->final_score, c->w_final.p, n));
+        FL_TRY(dl(c, o->passed_final, c->w_pfinal.p, n));
+    } else {
+        FL_TRY(dl(c, o->passed_final, c->w_passed.p, n));
+        if (o->norm_mean) memset(o->norm_mean, 0, n * sizeof(double));
+        if (o->norm_window) memset(o->norm_window, 0, n * sizeof(double));
+        if (o->final_score) memset(o->final_score, 0, n * sizeof(double));
+    }
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (o->length_score)
+        for (size_t i = 0; i < n; ++i) o->length_score[i] = host_length_score(e_host[i] - s_host[i]);
+    return FL_OK;
+}
+
+extern "C" int fl_results_pass_dev(fl_ctx *c, void **dev_passed_final, uint64_t *n_rows) {
+    if (!c || !dev_passed_final) return FL_EINVAL;
+    *dev_passed_final = c->finalized ? (void *)c->w_pfinal.p : (void *)c->w_passed.p;
+    if (n_rows) *n_rows = c->n_rows;
+    return FL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic workloads: integer-only, counter based -> identical on host and device
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ static inline unsigned long long fl_hash64(unsigned long long seed, unsigned long long a,
+                                                               unsigned long long b) {
+    unsigned long long x = seed + a * 0x9E3779B97F4A7C15ull + b * 0xD6E8FEB86659FD93ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+__host__ __device__ static inline uint8_t synth_qchar(unsigned long long seed, unsigned long long read, unsigned long long pos,
+                                                      int qbar) {
+    unsigned long long h = fl_hash64(seed, read, pos);
+    int s = (int)(h & 0xFF) + (int)((h >> 8) & 0xFF) + (int)((h >> 16) & 0xFF) + (int)((h >> 24) & 0xFF);   // ~N(510, 147.8^2)
+    int z = ((s - 510) * 111 + 2048) >> 12;                                                                  // ~N(0, 4^2), integer only
+    int q = qbar + z;
+    q = q < 1 ? 1 : (q > 50 ? 50 : q);
+    return (uint8_t)(q + 33);
+}
+
+__global__ void k_synth_qual(unsigned long long seed, uint32_t n, const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
+                             const uint8_t *__restrict__ qbar, unsigned long long read_base, uint8_t *__restrict__ qual) {
+    // one warp per read, lanes stride over 16-byte groups
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp; r < n; r += n_warps) {
+        const int L = len[r];
+        const int qb = qbar[r];
+        uint8_t *q = qual + off[r];
+        const int groups = (L + 15) >> 4;
+        for (int g = lane; g < groups; g += 32) {
+            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int pos = g * 16 + i;
+                uint8_t ch = pos < L ? synth_qchar(seed, read_base + r, (unsigned long long)pos, qb) : 0;
+                w[i >> 2] |= (uint32_t)ch << (8 * (i & 3));
+            }
+            reinterpret_cast<uint4 *>(q)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+extern "C" int fl_synth_qual_device(fl_ctx *c, uint64_t seed, uint32_t n, const uint64_t *dev_off, const int32_t *dev_len,
+                                    const uint8_t *dev_qbar, uint64_t read_index_base, uint8_t *dev_qual) {
+    if (!c) return FL_EINVAL;
+    if (n == 0) return FL_OK;
+    k_synth_qual<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, n, dev_off, dev_len, dev_qbar, read_index_base, dev_qual);
+    FL_CUDA(c, cudaGetLastError());
+    return FL_OK;
+}
+
+extern "C" void fl_synth_qual_host(uint64_t seed, uint32_t n, const uint64_t *off, const int32_t *len, const uint8_t *qbar,
+                                   uint64_t read_index_base, uint8_t *qual) {
+    for (uint32_t r = 0; r < n; ++r)
+        for (int pos = 0; pos < len[r]; ++pos)
+            qual[off[r] + pos] = synth_qchar(seed, read_index_base + r, (unsigned long long)pos, qbar[r]);
+}
+
+#define FL_SYNTH_GENOME_STREAM 0x47454E4F4D45ull
+
+__host__ __device__ static inline uint32_t synth_genome_word(unsigned long long seed, unsigned long long w) {
+    return (uint32_t)(fl_hash64(seed, FL_SYNTH_GENOME_STREAM, w) >> 16);
+}
+
+__global__ void k_synth_genome(unsigned long long seed, unsigned long long n_bases, uint32_t *__restrict__ out) {
+    const unsigned long long words = (n_bases + 15) >> 4;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words;
+         w += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t v = synth_genome_word(seed, w);
+        unsigned long long rem = n_bases - (w << 4);
+        if (rem < 16) v &= ~(0xFFFFFFFFu >> (2 * rem));     // bases beyond the end stay 0
+        out[w] = v;
+    }
+}
+
+extern "C" int fl_synth_genome_device(fl_ctx *c, uint64_t seed, uint64_t n_bases, uint32_t *dev_seq2b) {
+    if (!c) return FL_EINVAL;
+    k_synth_genome<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, n_bases, dev_seq2b);
+    FL_CUDA(c, cudaGetLastError());
+    return FL_OK;
+}
+
+extern "C" void fl_synth_genome_host(uint64_t seed, uint64_t n_bases, uint32_t *seq2b) {
+    const uint64_t words = (n_bases + 15) >> 4;
+    for (uint64_t w = 0; w < words; ++w) {
+        uint32_t v = synth_genome_word(seed, w);
+        uint64_t rem = n_bases - (w << 4);
+        if (rem < 16) v &= ~(0xFFFFFFFFu >> (2 * rem));
+        seq2b[w] = v;
+    }
+}
+
+__host__ __device__ static inline uint32_t genome_code(const uint32_t *g, unsigned long long pos) {
+    return (g[pos >> 4] >> (30 - 2 * (pos & 15))) & 3u;
+}
+
+__host__ __device__ static inline uint32_t synth_read_code(unsigned long long seed, const uint32_t *genome, unsigned long long start,
+                                                           int len, int strand, uint32_t err_ppm, int junk_pos, int junk_len,
+                                                           unsigned long long read, int i) {
+    unsigned long long h = fl_hash64(seed, read, (unsigned long long)i);
+    if (junk_len > 0 && i >= junk_pos && i < junk_pos + junk_len) return (uint32_t)(h >> 40) & 3u;
+    uint32_t code = strand ? 3u - genome_code(genome, start + (unsigned long long)(len - 1 - i)) : genome_code(genome, start + (unsigned long long)i);
+    unsigned long long thr = ((unsigned long long)err_ppm << 20) / 1000000ull;
+    if (((h >> 8) & 0xFFFFFull) < thr) code = (code + 1u + (uint32_t)((h >> 32) % 3ull)) & 3u;
+    return code;
+}
+
+__global__ void k_synth_reads(unsigned long long seed, const uint32_t *__restrict__ genome, fl_synth_reads d,
+                              unsigned long long read_base, uint32_t *__restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp; r < d.n; r += n_warps) {
+        const int L = d.len[r];
+        const unsigned long long st = d.start[r];
+        const int strand = d.strand[r];
+        const uint32_t err = d.err_ppm[r];
+        const int jp = d.junk_pos[r], jl = d.junk_len[r];
+        uint32_t *o = out + (d.off[r] >> 4);
+        const int words = L > 0 ? (int)((((unsigned)L + 63u) & ~63u) >> 4) : 0;
+        for (int w = lane; w < words; w += 32) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                int i = w * 16 + k;
+                if (i < L) v |= synth_read_code(seed, genome, st, L, strand, err, jp, jl, read_base + r, i) << (30 - 2 * k);
+            }
+            o[w] = v;
+        }
+    }
+}
+
+extern "C" int fl_synth_reads_device(fl_ctx *c, uint64_t seed, const uint32_t *dev_genome2b, const fl_synth_reads *dev_desc,
+                                     uint64_t read_index_base, uint32_t *dev_seq2b) {
+    if (!c || !dev_desc) return FL_EINVAL;
+    if (dev_desc->n == 0) return FL_OK;
+    k_synth_reads<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, dev_genome2b, *dev_desc, read_index_base, dev_seq2b);
+    FL_CUDA(c, cudaGetLastError());
+    return FL_OK;
+}
+
+extern "C" void fl_synth_reads_host(uint64_t seed, const uint32_t *genome2b, const fl_synth_reads *d, uint64_t read_index_base,
+                                    uint32_t *seq2b) {
+    for (uint32_t r = 0; r < d->n; ++r) {
+        const int L = d->len[r];
+        uint32_t *o = seq2b + (d->off[r] >> 4);
+        const int words = (int)(fl_padded_len(L) >> 4);
+        for (int w = 0; w < words; ++w) {
+            uint32_t v = 0;
+            for (int k = 0; k < 16; ++k) {
+                int i = w * 16 + k;
+                if (i < L)
+                    v |= synth_read_code(seed, genome2b, d->start[r], L, d->strand[r], d->err_ppm[r], d->junk_pos[r], d->junk_len[r],
+                                         read_index_base + r, i) << (30 - 2 * k);
+            }
+            o[w] = v;
+        }
+    }
+}

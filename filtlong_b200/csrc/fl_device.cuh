@@ -1,0 +1,78 @@
+// filtlong_b200/csrc/fl_device.cuh -- device helpers shared by the k-mer build and probe kernels.
+#pragma once
+#include "fl_internal.cuh"
+
+// A warp walks a sequence in steps of 1024 bases: lane l owns bases [32 l, 32 l + 32) of the step.
+// Work is cut into tiles of FL_TILE_BASES bases of ONE sequence so that long and short sequences
+// load-balance; tile_start[] is the exclusive scan of tiles-per-sequence.
+#define FL_STEP_BASES 1024
+#define FL_TILE_STEPS 8
+#define FL_TILE_BASES (FL_STEP_BASES * FL_TILE_STEPS)
+
+__device__ __forceinline__ unsigned long long fl_tiles_of(int len) {
+    return len <= 0 ? 0ull : ((unsigned long long)len + FL_TILE_BASES - 1) / FL_TILE_BASES;
+}
+
+// largest i in [0, n) with tile_start[i] <= t   (tile_start is non-decreasing, tile_start[0] == 0)
+__device__ __forceinline__ uint32_t fl_find_seq(const unsigned long long *__restrict__ tile_start, uint32_t n,
+                                                unsigned long long t) {
+    uint32_t lo = 0, hi = n;   // invariant: tile_start[lo] <= t, (hi == n or tile_start[hi] > t)
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (tile_start[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// The three 32-bit words a lane needs for its 32 forward 16-mers: w0 = bases 0..15 of its run,
+// w1 = bases 16..31, w2 = the first 16 bases after its run (owned by the next lane / next step).
+struct LaneWords {
+    uint32_t w0, w1, w2;
+};
+
+// seqw: the sequence's first word; step_base: first base of this step (multiple of 1024);
+// padded_len: padded length of the sequence (words beyond it must not be touched).
+__device__ __forceinline__ LaneWords fl_load_lane_words(const uint32_t *__restrict__ seqw, unsigned long long step_base,
+                                                        unsigned long long padded_len, unsigned lane) {
+    LaneWords r;
+    unsigned long long b = step_base + 32ull * lane;
+    uint2 v = make_uint2(0u, 0u);
+    if (b < padded_len) v = __ldg(reinterpret_cast<const uint2 *>(seqw + (b >> 4)));
+    r.w0 = v.x;
+    r.w1 = v.y;
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, r.w0, 1);
+    if (lane == 31) {
+        unsigned long long nb = step_base + FL_STEP_BASES;
+        nxt = (nb < padded_len) ? __ldg(seqw + (nb >> 4)) : 0u;
+    }
+    r.w2 = nxt;
+    return r;
+}
+
+// forward 16-mer starting at position p (0..31) of the lane's run (kmers.cpp:222-229 encoding:
+// first base in bits 31:30)
+__device__ __forceinline__ uint32_t fl_kmer_at(const LaneWords &w, int p) {
+    return p < 16 ? __funnelshift_l(w.w1, w.w0, 2 * p) : __funnelshift_l(w.w2, w.w1, 2 * (p - 16));
+}
+
+// reverse the order of the sixteen 2-bit fields of x
+__device__ __forceinline__ uint32_t fl_reverse_pairs(uint32_t x) {
+    uint32_t b = __brev(x);
+    return ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+}
+
+// spread the low 16 bits of x to the even bit positions
+__device__ __forceinline__ uint32_t fl_spread16(uint32_t x) {
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// Bloom hash j of a 4-byte key: bloom_filter.h:569-583 specialised (see oracle for derivation)
+__device__ __forceinline__ uint32_t fl_bloom_hash(uint32_t kmer, uint32_t salt) {
+    return salt ^ ~((salt << 11) + (kmer ^ (salt >> 5)));
+}

@@ -1,0 +1,177 @@
+// filtlong_b200/csrc/fl_internal.cuh -- shared declarations of the CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/filtlong_b200.h"
+
+#define FL_BLOOM_BITS 1917295480ull   // bloom_filter.h:108-160 with kmers.cpp:32-34's parameters
+#define FL_BLOOM_K 13
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: CUDA failures become FL_ECUDA + message, never exceptions
+// ---------------------------------------------------------------------------------------------
+#define FL_CUDA(ctx, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (ctx)->set_error(std::string(#call) + ": " + cudaGetErrorString(e__));             \
+            return FL_ECUDA;                                                                   \
+        }                                                                                      \
+    } while (0)
+
+#define FL_TRY(expr)                \
+    do {                            \
+        int rc__ = (expr);          \
+        if (rc__ != FL_OK) return rc__; \
+    } while (0)
+
+// A grow-only device array. Growth synchronises the stream, so steady-state batches (same or
+// smaller size than the largest seen) never allocate.
+template <typename T>
+struct DevVec {
+    T *p = nullptr;
+    size_t cap = 0;
+    ~DevVec() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // ensure capacity >= n elements, preserving the first `keep` elements
+    cudaError_t reserve(size_t n, size_t keep, cudaStream_t s) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = cap * 2 > n ? cap * 2 : n;
+        if (ncap < 1024) ncap = 1024;
+        T *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p) {
+            e = cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        if (p) cudaFree(p);
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+};
+
+// Device-side view of a batch (all pointers device memory).
+struct BatchView {
+    uint32_t n;
+    uint64_t padded_bases;
+    const uint64_t *off;
+    const int32_t *len;
+    const uint32_t *seq2b;
+    const uint8_t *qual;
+    const uint32_t *nmask;
+};
+
+// State of the weighted radix select, lives in device memory (one instance per context).
+struct SelectState {
+    unsigned long long prefix;       // key bits decided so far (most significant digits)
+    unsigned long long cum_before;   // passed bases (all ranks) with a strictly better key prefix
+    long long target;                // main.cpp:229-237
+    long long passed_bases;          // global
+    long long total_bases;           // global
+    int status;                      // fl_summary.status
+    int active;                      // 1 while digits are still being resolved
+    unsigned long long tie_key;      // full key of the tie class at the cut-off
+    unsigned long long tie_base;     // bases the tie class may still take: target - cum_before
+};
+
+struct fl_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    fl_params p{};
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    // ---- Kmers ----
+    uint32_t *d_bitmap = nullptr;        // 2^32 bits, direct-address membership
+    uint64_t n_kmers = 0;
+    bool kmers_count_stale = false;
+    // multiple-copy build state (kmers.cpp:142-166 in closed form, see fl_kmers.cu)
+    uint32_t *d_seen[4] = {nullptr, nullptr, nullptr, nullptr};   // ">= 1,2,3,4 sightings" bitmaps
+    unsigned long long *d_tfirst = nullptr;    // first add-stream index per k-mer (2^32 entries)
+    unsigned long long *d_bittime = nullptr;   // first time each Bloom bit was set
+    uint64_t add_counter = 0;                  // global add-stream index (kmers.cpp:109-120 order)
+    bool multi_pending = false;
+    unsigned long long *d_count_scratch = nullptr;
+
+    // ---- Phred LUTs ----
+    double *d_lut = nullptr;   // [0..256) q, [256..512) a = q / window_size
+    int lut_window = -1;
+
+    // ---- staging for host batches ----
+    DevVec<uint64_t> st_off;
+    DevVec<int32_t> st_len;
+    DevVec<uint32_t> st_seq, st_nmask;
+    DevVec<uint8_t> st_qual;
+
+    // ---- per-batch scratch ----
+    DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer
+    DevVec<uint32_t> sc_order;       // rows in descending-length bucket order
+    DevVec<uint32_t> sc_tiles;       // tile descriptors for the probe kernel
+    DevVec<unsigned long long> sc_u64a, sc_u64b, sc_u64c;
+    DevVec<uint32_t> sc_u32a;
+    DevVec<unsigned long long> sc_scan;   // block sums of fl_exclusive_scan_u64
+    uint32_t *d_buckets = nullptr;         // 256 bucket counters + 256 cursors (fl_order_by_length)
+    unsigned long long *d_scalars = nullptr;   // small device scalars (counts, cursors)
+    unsigned long long *h_scalars = nullptr;   // pinned mirror
+
+    // ---- results: one entry per INPUT READ ----
+    uint64_t n_reads = 0;
+    int64_t total_bases = 0;
+    DevVec<int32_t> r_len, r_first, r_last, r_nbad, r_nchild;
+    DevVec<double> r_mean, r_window;
+    DevVec<uint8_t> r_passed;
+    DevVec<unsigned long long> r_rowstart;
+
+    // ---- results: one entry per reads2 ROW ----
+    uint64_t n_rows = 0;
+    DevVec<uint32_t> w_parent;
+    DevVec<int32_t> w_start, w_end;
+    DevVec<double> w_mean, w_window, w_nmean, w_nwindow, w_final;
+    DevVec<uint8_t> w_passed, w_pfinal;
+    DevVec<unsigned long long> w_key;
+    bool finalized = false;
+
+    // ---- finalize scratch ----
+    SelectState *d_sel = nullptr;
+    double *d_norm = nullptr;            // sums4, min1, max1, sq1 (+ padding)
+    unsigned long long *d_hist = nullptr;  // 256 bins + tie/keeping scalars
+    DevVec<double> sc_f64;
+
+    void set_error(const std::string &m) { err = m; }
+};
+
+static inline unsigned fl_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---- implemented in fl_scan.cu ----
+int fl_exclusive_scan_u64(fl_ctx *ctx, const unsigned long long *in, unsigned long long *out, size_t n,
+                          unsigned long long *total_dev /* may be null */);
+// rows 0..n-1 ordered by descending length bucket into order[] (lengths may be null when
+// start/end are given: length = end - start)
+int fl_order_by_length(fl_ctx *ctx, const int32_t *len, size_t n, uint32_t *order);
+
+// ---- implemented in fl_kmers.cu ----
+int fl_kmers_ensure_bitmap(fl_ctx *ctx);
+int fl_kmers_add_view(fl_ctx *ctx, const BatchView &b, int multi);
+int fl_kmers_recount(fl_ctx *ctx);
+
+// ---- implemented in fl_score.cu ----
+int fl_score_view(fl_ctx *ctx, const BatchView &b);
+
+// ---- implemented in fl_select.cu ----
+int fl_norm_select_free(fl_ctx *ctx);

@@ -1,0 +1,725 @@
+// filtlong_b200/csrc/fl_score.cu -- per-read scoring, replaces Read::Read (reference src/read.cpp:25-144).
+//
+// Two modes, chosen by the state of the k-mer set exactly like read.cpp:35 (`kmers->empty()`):
+//
+//  Phred mode (read.cpp:35-39): one THREAD per read walks the quality string in the reference's
+//    own operation order -- sum += q[c] for the mean (read.cpp:208-213), and the incremental
+//    window recurrence w -= a[c_out]; w += a[c_in] (read.cpp:216-236) -- so mean and window
+//    quality come out bit-identical to the reference (their rounding depends on the order of
+//    the additions). q[] and a[] = q[]/window_size are 256-entry tables evaluated with the host
+//    libm (read.cpp:270-273) and replicated in shared memory so that every lane owns its banks.
+//    Rows are issued longest-first (length buckets) so lanes of a warp carry similar work.
+//
+//  k-mer mode (read.cpp:43-58): kernel A is the HBM-bound hot loop -- a warp streams 1024 bases
+//    per step (coalesced 8-byte loads of 2-bit codes), forms the 32 forward 16-mers of each lane
+//    with funnel shifts, probes the 512 MiB direct-address bitmap (one 32-byte sector per base
+//    when the set exceeds L2), and paints 16-base hits into a 1-bit-per-base mask with shuffles.
+//    Kernels B then work on that mask only (L/8 bytes per read): popcount -> mean (exact: the
+//    reference sums 1.0s), first/last base in a k-mer (read.cpp:75-84), bad ranges and child
+//    ranges (read.cpp:89-130), and the serial window recurrence on {0, 1/ws} per row. Children
+//    are NOT re-probed: a matching 16-mer never overlaps a bad range, so a child's mask is the
+//    parent's mask restricted to the child range; the reference re-runs the whole
+//    constructor instead (read.cpp:137).
+#include "fl_device.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// shared scalar helpers (double arithmetic in exactly the reference's order; file is compiled
+// with --fmad=false so nothing is contracted)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double length_score(int length) {          // read.cpp:241-244
+    const double half = 5000.0;
+    return 100.0 * (1.0 + (-half / ((double)length + half)));
+}
+
+__device__ __forceinline__ uint8_t hard_cutoffs(const fl_params &p, int length, double mean_q, double window_q) {
+    if (p.min_length_set && length < p.min_length) return 0;           // read.cpp:65-73 (else-if chain)
+    else if (p.max_length_set && length > p.max_length) return 0;
+    else if (p.min_mean_q_set && mean_q < p.min_mean_q) return 0;
+    else if (p.min_window_q_set && window_q < p.min_window_q) return 0;
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phred mode
+// ---------------------------------------------------------------------------------------------
+struct PhredArgs {
+    const uint8_t *qual;
+    const uint64_t *off;
+    const int32_t *len;
+    const uint32_t *order;
+    uint32_t n;
+    const double *lut;          // [512]
+    fl_params p;
+    // outputs, already offset to this batch's first read / row
+    int32_t *r_len, *r_first, *r_last, *r_nbad, *r_nchild;
+    double *r_mean, *r_window;
+    uint8_t *r_passed;
+    unsigned long long *r_rowstart;
+    uint32_t *w_parent;
+    int32_t *w_start, *w_end;
+    double *w_mean, *w_window;
+    uint8_t *w_passed;
+    unsigned long long read_base, row_base;
+};
+
+#define PHRED_THREADS 256
+#define PHRED_SMEM (256 * 8 * 16 + 256 * 16 * 8)   // {q,a} x 8 copies + a x 16 copies = 64 KiB
+
+__device__ __forceinline__ void phred_step(unsigned cin, unsigned cout, const double2 *tqa, const double *ta,
+                                           double &sum, double &w, double &best) {
+    double2 qa = tqa[cin * 8];
+    double ao = ta[cout * 16];
+    sum += qa.x;                 // read.cpp:210-211
+    w -= ao;                     // read.cpp:229
+    w += qa.y;                   // read.cpp:230
+    if (w < best) best = w;      // read.cpp:231-232
+}
+
+__device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+template <int WI>
+__device__ __forceinline__ void out_words(const uint4 &a, const uint4 &b, unsigned sh, uint32_t ow[4]) {
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ow[k] = __funnelshift_r(c[WI + k], c[WI + k + 1], sh);
+}
+
+__global__ void __launch_bounds__(PHRED_THREADS, 3) k_score_phred(PhredArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *tqa_all = reinterpret_cast<double2 *>(smem_raw);                       // [256][8]
+    double *ta_all = reinterpret_cast<double *>(smem_raw + 256 * 8 * 16);           // [256][16]
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        int c = i >> 3;
+        tqa_all[i] = make_double2(a.lut[c], a.lut[256 + c]);
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) ta_all[i] = a.lut[256 + (i >> 4)];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const double2 *tqa = tqa_all + (lane & 7);    // lane-private 16-byte bank group
+    const double *ta = ta_all + (lane & 15);      // lane-private 8-byte bank pair
+    const int ws = a.p.window_size;
+    const double wsd = (double)ws;
+
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n; it += T) {
+        const uint32_t r = a.order[it];
+        const int L = a.len[r];
+        const uint8_t *q = a.qual + a.off[r];
+        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
+        double sum = 0.0;
+        const int head = L < ws ? L : ws;
+        int j = 0;
+        // first window: only the running sum (it is both the mean's prefix and the first window's sum)
+        for (; j + 16 <= head; j += 16) {
+            uint4 v = __ldg(qv + (j >> 4));
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) sum += tqa[byte_of(wv[k], b) * 8].x;
+        }
+        for (; j < head; ++j) sum += tqa[(unsigned)q[j] * 8].x;
+
+        double mean, window;
+        if (L <= ws) {                                   // read.cpp:217-218
+            mean = 100.0 * sum / (double)L;
+            window = mean;
+        } else {
+            double w = sum / wsd;                        // read.cpp:223
+            double best = w;
+            for (; (j & 15) && j < L; ++j) phred_step(q[j], q[j - ws], tqa, ta, sum, w, best);
+            if (j + 16 <= L) {
+                const int i0 = j - ws;                   // >= 0
+                int blk = i0 >> 4;
+                const unsigned s = (unsigned)(i0 & 15);  // constant for the whole launch
+                const unsigned sh = (s & 3u) * 8u;
+                const unsigned wi = s >> 2;
+                uint4 oa = __ldg(qv + blk);
+                for (; j + 16 <= L; j += 16) {
+                    uint4 in = __ldg(qv + (j >> 4));
+                    uint4 ob = __ldg(qv + blk + 1);
+                    uint32_t ow[4];
+                    switch (wi) {
+                        case 0: out_words<0>(oa, ob, sh, ow); break;
+                        case 1: out_words<1>(oa, ob, sh, ow); break;
+                        case 2: out_words<2>(oa, ob, sh, ow); break;
+                        default: out_words<3>(oa, ob, sh, ow); break;
+                    }
+                    const uint32_t iw[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            phred_step(byte_of(iw[k], b), byte_of(ow[k], b), tqa, ta, sum, w, best);
+                    oa = ob;
+                    ++blk;
+                }
+            }
+            for (; j < L; ++j) phred_step(q[j], q[j - ws], tqa, ta, sum, w, best);
+            if (best < 0.5 / wsd) best = 0.0;            // read.cpp:233-234
+            window = 100.0 * best;
+            mean = 100.0 * sum / (double)L;
+        }
+        const uint8_t passed = hard_cutoffs(a.p, L, mean, window);
+        a.r_len[r] = L;
+        a.r_mean[r] = mean;
+        a.r_window[r] = window;
+        a.r_passed[r] = passed;
+        a.r_first[r] = -1;                               // read.cpp:75-76 (only set in k-mer mode)
+        a.r_last[r] = -1;
+        a.r_nbad[r] = 0;
+        a.r_nchild[r] = 0;
+        a.r_rowstart[r] = a.row_base + r;
+        a.w_parent[r] = (uint32_t)(a.read_base + r);
+        a.w_start[r] = 0;
+        a.w_end[r] = L;
+        a.w_mean[r] = mean;
+        a.w_window[r] = window;
+        a.w_passed[r] = passed;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-mer mode, kernel A: probe + paint
+// ---------------------------------------------------------------------------------------------
+struct ProbeArgs {
+    const uint32_t *seq2b;
+    const uint64_t *off;
+    const int32_t *len;
+    const unsigned long long *tile_start;   // [n+1]
+    uint32_t n;
+    unsigned long long n_tiles;
+    const uint32_t *bitmap;
+    uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
+};
+
+__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t kmer) {
+    return __ldg(bitmap + (kmer >> 5));
+}
+
+__global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long tile = warp; tile < a.n_tiles; tile += n_warps) {
+        const uint32_t s = fl_find_seq(a.tile_start, a.n, tile);
+        const int L = a.len[s];
+        const unsigned long long off = a.off[s];
+        const uint32_t *seqw = a.seq2b + (off >> 4);
+        uint32_t *maskw = a.mask + (off >> 5);
+        const unsigned long long padded = ((unsigned long long)L + FL_ALIGN_BASES - 1) & ~(unsigned long long)(FL_ALIGN_BASES - 1);
+        const unsigned long long tile_base = (tile - a.tile_start[s]) * FL_TILE_BASES;
+
+        // hits of the 16 k-mer starts just before the tile (they paint into the tile's first bases)
+        uint32_t carry = 0;   // bit k = hit of the k-mer starting at base (run_start - 32 + k)
+        if (tile_base > 0) {
+            uint32_t wa = __ldg(seqw + (tile_base >> 4) - 1), wb = __ldg(seqw + (tile_base >> 4));
+            uint32_t hit = 0;
+            if (lane < 16) {
+                unsigned long long b = tile_base - 16 + lane;
+                if (b + (FL_K - 1) < (unsigned long long)L) {
+                    uint32_t k = __funnelshift_l(wb, wa, 2 * lane);
+                    hit = (probe(a.bitmap, k) >> (k & 31)) & 1u;
+                }
+            }
+            carry = __ballot_sync(0xffffffffu, hit) << 16;
+        }
+        for (int step = 0; step < FL_TILE_STEPS; ++step) {
+            const unsigned long long sb = tile_base + (unsigned long long)step * FL_STEP_BASES;
+            if (sb >= padded) break;
+            const LaneWords w = fl_load_lane_words(seqw, sb, padded, lane);
+            const unsigned long long lb = sb + 32ull * lane;
+            // number of valid k-mer starts in this lane's run: starts b with b + 15 < L
+            long long nv = (long long)L - (FL_K - 1) - (long long)lb;
+            const int nvalid = nv <= 0 ? 0 : (nv >= 32 ? 32 : (int)nv);
+            uint32_t h = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t words[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int p = half * 16 + i;
+                    const uint32_t k = fl_kmer_at(w, p);
+                    words[i] = (p < nvalid) ? probe(a.bitmap, k) : 0u;     // read.cpp:52
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int p = half * 16 + i;
+                    const uint32_t k = fl_kmer_at(w, p);
+                    h |= ((words[i] >> (k & 31)) & 1u) << p;
+                }
+            }
+            // paint: base covered if any of the 16 k-mers ending at or after it hit (read.cpp:53-54)
+            uint32_t prev = __shfl_up_sync(0xffffffffu, h, 1);
+            if (lane == 0) prev = carry;
+            unsigned long long y = ((unsigned long long)h << 32) | prev;
+            y |= y << 1;
+            y |= y << 2;
+            y |= y << 4;
+            y |= y << 8;
+            if (lb < padded) maskw[lb >> 5] = (uint32_t)(y >> 32);
+            carry = __shfl_sync(0xffffffffu, h, 31);
+        }
+    }
+}
+
+__global__ void k_tiles_of(const int32_t *__restrict__ len, uint32_t n, unsigned long long *__restrict__ tiles) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tiles[i] = fl_tiles_of(len[i] > 0 ? (int)(((unsigned)len[i] + FL_ALIGN_BASES - 1) & ~(FL_ALIGN_BASES - 1)) : 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-mer mode, kernels B: everything else from the 1-bit mask
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_next(const uint32_t *__restrict__ m, int p, int end, bool want_one) {
+    while (p < end) {
+        uint32_t w = m[p >> 5];
+        if (!want_one) w = ~w;
+        w &= 0xFFFFFFFFu << (p & 31);
+        if (w) {
+            int q = (p & ~31) + __ffs(w) - 1;
+            return q < end ? q : end;
+        }
+        p = (p & ~31) + 32;
+    }
+    return end;
+}
+
+// Walks the bad ranges of read.cpp:89-117 in order and reports child ranges (read.cpp:119-130).
+// F(start, end, child_index). Returns n_child; *n_bad_out = m_bad_ranges.size().
+template <typename F>
+__device__ __forceinline__ int enumerate_children(const uint32_t *__restrict__ m, int L, int first, int last,
+                                                  const fl_params &p, int *n_bad_out, F emit) {
+    int n_bad = 0, n_child = 0, rs = 0;
+    auto bad = [&](int s, int e) {
+        ++n_bad;
+        if (s - rs > 0) emit(rs, s, n_child++);
+        rs = e;
+    };
+    if (first < 0) {
+        // no base is in a k-mer: one zero run [0, L); trimming adds nothing (read.cpp:107,112)
+        if (p.split_set && L > 0 && L >= p.split) bad(0, L);
+    } else {
+        const bool lead_is_split = p.split_set && first >= p.split && first > 0;
+        const bool tail_is_split = p.split_set && (L - last) >= p.split && last < L;
+        if (lead_is_split) bad(0, first);
+        else if (p.trim && first > 0) bad(0, first);                     // read.cpp:107-111
+        if (p.split_set) {                                               // read.cpp:89-103, runs inside [first, last)
+            int i = first;
+            while (i < last) {
+                int z = find_next(m, i, last, false);
+                if (z >= last) break;
+                int o = find_next(m, z, last, true);
+                if (o - z >= p.split) bad(z, o);
+                i = o;
+            }
+        }
+        if (tail_is_split) bad(last, L);
+        else if (p.trim && last < L) bad(last, L);                       // read.cpp:112-116
+    }
+    if (n_bad > 0 && L - rs > 0) emit(rs, L, n_child++);                 // read.cpp:127-129
+    *n_bad_out = n_bad;
+    return n_child;
+}
+
+struct KmerArgs {
+    const uint32_t *mask;
+    const uint64_t *off;
+    const int32_t *len;
+    uint32_t n;
+    fl_params p;
+    int32_t *r_len, *r_first, *r_last, *r_nbad, *r_nchild;
+    double *r_mean, *r_window;
+    uint8_t *r_passed;
+    unsigned long long *r_rowstart;
+    unsigned long long *rows_per_read;   // scratch [n]
+    unsigned long long read_base, row_base;
+};
+
+// B1: per read -- first/last base in a k-mer, number of bad ranges and children
+__global__ void __launch_bounds__(256) k_kmer_ranges(KmerArgs a) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    const int L = a.len[r];
+    const uint32_t *m = a.mask + (a.off[r] >> 5);
+    int first = -1, last = -1;
+    const int nw = (L + 31) >> 5;
+    for (int w = 0; w < nw; ++w) {                       // read.cpp:77-84
+        uint32_t x = m[w];
+        if (x) {
+            if (first < 0) first = (w << 5) + __ffs(x) - 1;
+            last = (w << 5) + 32 - __clz(x);
+        }
+    }
+    int n_bad = 0, n_child = 0;
+    if (a.p.trim || a.p.split_set)
+        n_child = enumerate_children(m, L, first, last, a.p, &n_bad, [](int, int, int) {});
+    a.r_len[r] = L;
+    a.r_first[r] = first;
+    a.r_last[r] = last;
+    a.r_nbad[r] = n_bad;
+    a.r_nchild[r] = n_child;
+    a.rows_per_read[r] = n_child > 0 ? (unsigned long long)n_child : 1ull;
+    a.r_rowstart[r] = a.row_base + r;   // final when nothing can have children; else replaced by the scan
+}
+
+// B2: per read -- row descriptors (children, or the read itself)
+struct RowArgs {
+    const uint32_t *mask;
+    const uint64_t *off;
+    const int32_t *len;
+    uint32_t n;
+    fl_params p;
+    const int32_t *r_first, *r_last, *r_nchild;
+    unsigned long long *r_rowstart;             // in: exclusive scan of rows per read (batch-local); out: + row_base
+    uint32_t *w_parent;                         // offset to this batch's first row
+    int32_t *w_start, *w_end, *w_len;
+    unsigned long long read_base, row_base;
+};
+
+__global__ void __launch_bounds__(256) k_kmer_rows(RowArgs a) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    const int L = a.len[r];
+    const unsigned long long rs = a.r_rowstart[r];
+    a.r_rowstart[r] = rs + a.row_base;
+    if (a.r_nchild[r] == 0) {
+        a.w_parent[rs] = (uint32_t)(a.read_base + r);
+        a.w_start[rs] = 0;
+        a.w_end[rs] = L;
+        a.w_len[rs] = L;
+        return;
+    }
+    const uint32_t *m = a.mask + (a.off[r] >> 5);
+    int nb;
+    enumerate_children(m, L, a.r_first[r], a.r_last[r], a.p, &nb, [&](int s, int e, int c) {
+        a.w_parent[rs + c] = (uint32_t)(a.read_base + r);
+        a.w_start[rs + c] = s;
+        a.w_end[rs + c] = e;
+        a.w_len[rs + c] = e - s;
+    });
+}
+
+// B3: per row -- mean and window quality from the mask range [S, E) of the parent read.
+// The k-mer-mode quality of a base is exactly 0.0 or 1.0 (read.cpp:42,55), so the mean's sequential
+// sum is an exact integer, and the window recurrence adds / subtracts r = 1.0 / ws or 0.0 in the
+// reference's order (read.cpp:226-232) -- bit-identical, including its rounding drift.
+__device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, int S, int E, int ws, double *mean_out,
+                                               double *window_out) {
+    const int len = E - S;
+    // popcount of [S, E)
+    long long hits = 0;
+    {
+        int p = S;
+        while (p < E) {
+            uint32_t w = m[p >> 5] & (0xFFFFFFFFu << (p & 31));
+            int wend = (p & ~31) + 32;
+            if (wend > E) w &= 0xFFFFFFFFu >> (wend - E);
+            hits += __popc(w);
+            p = wend;
+        }
+    }
+    const double mean = 100.0 * (double)hits / (double)len;             // read.cpp:208-213
+    if (len <= ws) {                                                     // read.cpp:217-218
+        *mean_out = mean;
+        *window_out = mean;
+        return;
+    }
+    const double wsd = (double)ws;
+    const double rq = 1.0 / wsd;                                         // qualities[i] / window_size with q == 1.0
+    long long c0 = 0;
+    {
+        int p = S;
+        const int e0 = S + ws;
+        while (p < e0) {
+            uint32_t w = m[p >> 5] & (0xFFFFFFFFu << (p & 31));
+            int wend = (p & ~31) + 32;
+            if (wend > e0) w &= 0xFFFFFFFFu >> (wend - e0);
+            c0 += __popc(w);
+            p = wend;
+        }
+    }
+    double w = (double)c0 / wsd;                                         // read.cpp:220-223
+    double best = w;
+    int pin = S + ws, pout = S;
+    // scalar steps until the incoming position is word aligned
+    auto step = [&](unsigned bin, unsigned bout) {
+        w -= bout ? rq : 0.0;                                            // read.cpp:229
+        w += bin ? rq : 0.0;                                             // read.cpp:230
+        if (w < best) best = w;
+    };
+    for (; (pin & 31) && pin < E; ++pin, ++pout)
+        step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
+    if (pin + 32 <= E) {
+        const unsigned sh = (unsigned)(pout & 31);       // constant from here on
+        int ow_idx = pout >> 5;
+        uint32_t olo = m[ow_idx];
+        for (; pin + 32 <= E; pin += 32, pout += 32) {
+            const uint32_t inw = m[pin >> 5];
+            const uint32_t ohi = m[ow_idx + 1];          // within the parent's padded mask: pout + 32 + 31 < pin + 32 <= E
+            const uint32_t outw = __funnelshift_r(olo, ohi, sh);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) step((inw >> t) & 1u, (outw >> t) & 1u);
+            olo = ohi;
+            ++ow_idx;
+        }
+    }
+    for (; pin < E; ++pin, ++pout)
+        step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
+    if (best < 0.5 / wsd) best = 0.0;                                    // read.cpp:233-234
+    *mean_out = mean;
+    *window_out = 100.0 * best;
+}
+
+struct StatArgs {
+    const uint32_t *mask;
+    const uint64_t *off;          // per batch read
+    const uint32_t *order;        // rows in descending length order
+    uint32_t n_rows;
+    fl_params p;
+    // rows (batch-local indexing): parent is a GLOBAL read index; read_base converts to batch-local
+    const uint32_t *w_parent;
+    const int32_t *w_start, *w_end;
+    double *w_mean, *w_window;
+    uint8_t *w_passed;
+    unsigned long long read_base;
+    // when non-null: rows that are whole reads copy the parent's statistics instead of recomputing
+    const int32_t *r_nchild;
+    const double *r_mean, *r_window;
+    const uint8_t *r_passed;
+};
+
+__global__ void __launch_bounds__(256) k_kmer_stats(StatArgs a) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n_rows; it += T) {
+        const uint32_t row = a.order[it];
+        const uint32_t r = (uint32_t)(a.w_parent[row] - a.read_base);
+        if (a.r_nchild && a.r_nchild[r] == 0) {
+            a.w_mean[row] = a.r_mean[r];
+            a.w_window[row] = a.r_window[r];
+            a.w_passed[row] = a.r_passed[r];
+            continue;
+        }
+        const int S = a.w_start[row], E = a.w_end[row];
+        const uint32_t *m = a.mask + (a.off[r] >> 5);
+        double mean, window;
+        kmer_row_stats(m, S, E, a.p.window_size, &mean, &window);
+        a.w_mean[row] = mean;
+        a.w_window[row] = window;
+        a.w_passed[row] = hard_cutoffs(a.p, E - S, mean, window);
+    }
+}
+
+__global__ void k_iota(uint32_t *p, uint32_t n, uint32_t base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = base + i;
+}
+
+__global__ void k_identity_rows(uint32_t n, const int32_t *__restrict__ len, uint32_t *w_parent, int32_t *w_start,
+                                int32_t *w_end, unsigned long long read_base) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    w_parent[i] = (uint32_t)(read_base + i);
+    w_start[i] = 0;
+    w_end[i] = len[i];
+}
+
+template <typename T>
+cudaError_t grow(DevVec<T> &v, size_t n, size_t keep, cudaStream_t s) { return v.reserve(n, keep, s); }
+
+}  // namespace
+
+static int reserve_reads(fl_ctx *c, size_t n_total) {
+    size_t k = c->n_reads;
+    cudaStream_t s = c->stream;
+    FL_CUDA(c, grow(c->r_len, n_total, k, s));
+    FL_CUDA(c, grow(c->r_first, n_total, k, s));
+    FL_CUDA(c, grow(c->r_last, n_total, k, s));
+    FL_CUDA(c, grow(c->r_nbad, n_total, k, s));
+    FL_CUDA(c, grow(c->r_nchild, n_total, k, s));
+    FL_CUDA(c, grow(c->r_mean, n_total, k, s));
+    FL_CUDA(c, grow(c->r_window, n_total, k, s));
+    FL_CUDA(c, grow(c->r_passed, n_total, k, s));
+    FL_CUDA(c, grow(c->r_rowstart, n_total, k, s));
+    return FL_OK;
+}
+
+static int reserve_rows(fl_ctx *c, size_t n_total) {
+    size_t k = c->n_rows;
+    cudaStream_t s = c->stream;
+    FL_CUDA(c, grow(c->w_parent, n_total, k, s));
+    FL_CUDA(c, grow(c->w_start, n_total, k, s));
+    FL_CUDA(c, grow(c->w_end, n_total, k, s));
+    FL_CUDA(c, grow(c->w_mean, n_total, k, s));
+    FL_CUDA(c, grow(c->w_window, n_total, k, s));
+    FL_CUDA(c, grow(c->w_passed, n_total, k, s));
+    return FL_OK;
+}
+
+static int ensure_lut(fl_ctx *ctx) {
+    if (ctx->d_lut && ctx->lut_window == ctx->p.window_size) return FL_OK;
+    double h[512];
+    fl_phred_luts(ctx->p.window_size, h, h + 256);
+    if (!ctx->d_lut) FL_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(h)));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->lut_window = ctx->p.window_size;
+    return FL_OK;
+}
+
+static int score_phred(fl_ctx *ctx, const BatchView &b) {
+    if (!b.qual) {
+        ctx->set_error("FASTA input not supported without an external reference (no quality string and the k-mer set is empty)");
+        return FL_EINVAL;                                   // main.cpp:103-106
+    }
+    FL_TRY(ensure_lut(ctx));
+    const size_t n = b.n;
+    FL_TRY(reserve_reads(ctx, ctx->n_reads + n));
+    FL_TRY(reserve_rows(ctx, ctx->n_rows + n));
+    FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, ctx->stream));
+    FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
+    PhredArgs a{};
+    a.qual = b.qual; a.off = b.off; a.len = b.len; a.order = ctx->sc_order.p; a.n = b.n;
+    a.lut = ctx->d_lut; a.p = ctx->p;
+    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+    a.r_len = ctx->r_len.p + rb; a.r_first = ctx->r_first.p + rb; a.r_last = ctx->r_last.p + rb;
+    a.r_nbad = ctx->r_nbad.p + rb; a.r_nchild = ctx->r_nchild.p + rb;
+    a.r_mean = ctx->r_mean.p + rb; a.r_window = ctx->r_window.p + rb; a.r_passed = ctx->r_passed.p + rb;
+    a.r_rowstart = ctx->r_rowstart.p + rb;
+    a.w_parent = ctx->w_parent.p + wb; a.w_start = ctx->w_start.p + wb; a.w_end = ctx->w_end.p + wb;
+    a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
+    a.read_base = rb; a.row_base = wb;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FL_CUDA(ctx, cudaFuncSetAttribute(k_score_phred, cudaFuncAttributeMaxDynamicSharedMemorySize, PHRED_SMEM));
+        attr_set = true;
+    }
+    unsigned blocks = fl_blocks(n, PHRED_THREADS);
+    unsigned max_blocks = (unsigned)ctx->sm_count * 3;
+    if (blocks > max_blocks) blocks = max_blocks;
+    k_score_phred<<<blocks, PHRED_THREADS, PHRED_SMEM, ctx->stream>>>(a);
+    ctx->launches++;
+    FL_CUDA(ctx, cudaGetLastError());
+    ctx->n_reads += n;
+    ctx->n_rows += n;
+    return FL_OK;
+}
+
+static int score_kmer(fl_ctx *ctx, const BatchView &b) {
+    if (!b.seq2b) { ctx->set_error("k-mer scoring needs seq2b"); return FL_EINVAL; }
+    const size_t n = b.n;
+    cudaStream_t st = ctx->stream;
+    FL_TRY(reserve_reads(ctx, ctx->n_reads + n));
+    // ---- kernel A: probe + paint ----
+    FL_CUDA(ctx, ctx->sc_mask.reserve((size_t)(b.padded_bases >> 5) + 1, 0, st));
+    FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, st));
+    k_tiles_of<<<fl_blocks(n, 256), 256, 0, st>>>(b.len, b.n, ctx->sc_u64a.p);
+    ctx->launches++;
+    FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64a.p, ctx->sc_u64a.p, n, ctx->d_scalars));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->sc_u64a.p + n, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(ctx, cudaStreamSynchronize(st));
+    const unsigned long long n_tiles = ctx->h_scalars[0];
+    if (n_tiles) {
+        ProbeArgs pa{};
+        pa.seq2b = b.seq2b; pa.off = b.off; pa.len = b.len; pa.tile_start = ctx->sc_u64a.p;
+        pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.mask = ctx->sc_mask.p;
+        unsigned blocks = (unsigned)((n_tiles + 7) / 8);
+        unsigned max_blocks = (unsigned)ctx->sm_count * 4;
+        if (blocks > max_blocks) blocks = max_blocks;
+        k_probe_paint<<<blocks, 256, 0, st>>>(pa);
+        ctx->launches++;
+        FL_CUDA(ctx, cudaGetLastError());
+    }
+    // ---- B1: ranges ----
+    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+    FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, st));
+    KmerArgs ka{};
+    ka.mask = ctx->sc_mask.p; ka.off = b.off; ka.len = b.len; ka.n = b.n; ka.p = ctx->p;
+    ka.r_len = ctx->r_len.p + rb; ka.r_first = ctx->r_first.p + rb; ka.r_last = ctx->r_last.p + rb;
+    ka.r_nbad = ctx->r_nbad.p + rb; ka.r_nchild = ctx->r_nchild.p + rb;
+    ka.r_mean = ctx->r_mean.p + rb; ka.r_window = ctx->r_window.p + rb; ka.r_passed = ctx->r_passed.p + rb;
+    ka.r_rowstart = ctx->r_rowstart.p + rb; ka.rows_per_read = ctx->sc_u64b.p;
+    ka.read_base = rb; ka.row_base = wb;
+    k_kmer_ranges<<<fl_blocks(n, 256), 256, 0, st>>>(ka);
+    ctx->launches++;
+    // ---- B3 on the parents (their own raw mean / window / passed: read.cpp:60-73) ----
+    FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
+    FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
+    FL_CUDA(ctx, ctx->sc_u32a.reserve(n, 0, st));
+    k_iota<<<fl_blocks(n, 256), 256, 0, st>>>(ctx->sc_u32a.p, b.n, (uint32_t)rb);   // parent of "row" i is read rb + i
+    ctx->launches++;
+    const unsigned stat_blocks_max = (unsigned)ctx->sm_count * 8;
+    {
+        StatArgs sa{};
+        sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.order = ctx->sc_order.p; sa.n_rows = b.n; sa.p = ctx->p;
+        sa.w_parent = ctx->sc_u32a.p;
+        // whole-read ranges: start 0, end len -> reuse r_len as "end" and a zero array for start
+        FL_CUDA(ctx, ctx->sc_u64c.reserve((n + 1) / 2 + 1, 0, st));
+        int32_t *zeros = reinterpret_cast<int32_t *>(ctx->sc_u64c.p);
+        FL_CUDA(ctx, cudaMemsetAsync(zeros, 0, n * sizeof(int32_t), st));
+        sa.w_start = zeros; sa.w_end = b.len;
+        sa.w_mean = ctx->r_mean.p + rb; sa.w_window = ctx->r_window.p + rb; sa.w_passed = ctx->r_passed.p + rb;
+        sa.read_base = rb;
+        unsigned blocks = fl_blocks(n, 256);
+        if (blocks > stat_blocks_max) blocks = stat_blocks_max;
+        k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        ctx->launches++;
+    }
+    // ---- rows ----
+    const bool may_have_children = ctx->p.trim || ctx->p.split_set;
+    size_t n_rows_batch = n;
+    if (may_have_children) {
+        FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64b.p, ctx->r_rowstart.p + rb, n, ctx->d_scalars));
+        FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        FL_CUDA(ctx, cudaStreamSynchronize(st));
+        n_rows_batch = (size_t)ctx->h_scalars[0];
+    }
+    FL_TRY(reserve_rows(ctx, ctx->n_rows + n_rows_batch));
+    if (!may_have_children) {
+        k_identity_rows<<<fl_blocks(n, 256), 256, 0, st>>>(b.n, b.len, ctx->w_parent.p + wb, ctx->w_start.p + wb,
+                                                          ctx->w_end.p + wb, rb);
+        ctx->launches++;
+        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_mean.p + wb, ctx->r_mean.p + rb, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_window.p + wb, ctx->r_window.p + rb, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_passed.p + wb, ctx->r_passed.p + rb, n, cudaMemcpyDeviceToDevice, st));
+    } else {
+        RowArgs ra{};
+        ra.mask = ctx->sc_mask.p; ra.off = b.off; ra.len = b.len; ra.n = b.n; ra.p = ctx->p;
+        ra.r_first = ctx->r_first.p + rb; ra.r_last = ctx->r_last.p + rb; ra.r_nchild = ctx->r_nchild.p + rb;
+        ra.r_rowstart = ctx->r_rowstart.p + rb;
+        ra.w_parent = ctx->w_parent.p + wb; ra.w_start = ctx->w_start.p + wb; ra.w_end = ctx->w_end.p + wb;
+        FL_CUDA(ctx, ctx->sc_u64c.reserve((n_rows_batch + 1) / 2 + 1, 0, st));
+        ra.w_len = reinterpret_cast<int32_t *>(ctx->sc_u64c.p);
+        ra.read_base = rb; ra.row_base = wb;
+        k_kmer_rows<<<fl_blocks(n, 256), 256, 0, st>>>(ra);
+        ctx->launches++;
+        FL_CUDA(ctx, ctx->sc_order.reserve(n_rows_batch, 0, st));
+        FL_TRY(fl_order_by_length(ctx, ra.w_len, n_rows_batch, ctx->sc_order.p));
+        StatArgs sa{};
+        sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.order = ctx->sc_order.p; sa.n_rows = (uint32_t)n_rows_batch; sa.p = ctx->p;
+        sa.w_parent = ctx->w_parent.p + wb; sa.w_start = ctx->w_start.p + wb; sa.w_end = ctx->w_end.p + wb;
+        sa.w_mean = ctx->w_mean.p + wb; sa.w_window = ctx->w_window.p + wb; sa.w_passed = ctx->w_passed.p + wb;
+        sa.read_base = rb;
+        sa.r_nchild = ctx->r_nchild.p + rb; sa.r_mean = ctx->r_mean.p + rb; sa.r_window = ctx->r_window.p + rb;
+        sa.r_passed = ctx->r_passed.p + rb;
+        unsigned blocks = fl_blocks(n_rows_batch, 256);
+        if (blocks > stat_blocks_max) blocks = stat_blocks_max;
+        k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        ctx->launches++;
+    }
+    FL_CUDA(ctx, cudaGetLastError());
+    ctx->n_reads += n;
+    ctx->n_rows += n_rows_batch;
+    return FL_OK;
+}
+
+int fl_score_view(fl_ctx *ctx, const BatchView &b) {
+    if (b.n == 0) return FL_OK;
+    if (ctx->kmers_count_stale || ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
+    ctx->finalized = false;
+    if (ctx->n_kmers == 0) return score_phred(ctx, b);     // read.cpp:35: kmers->empty()
+    return score_kmer(ctx, b);
+}

@@ -121,6 +121,9 @@ def lib():
         L.orc_bloom_hash.argtypes = [C.c_uint32, C.c_int]
         L.orc_bloom_hash.restype = C.c_uint32
         L.orc_bloom_table_bits.restype = C.c_uint64
+        for f in (L.orc_base_fwd, L.orc_base_rev):
+            f.argtypes = [C.c_char]
+            f.restype = C.c_uint32
         L.orc_qscore_to_quality.argtypes = [C.c_char]
         L.orc_qscore_to_quality.restype = C.c_double
         L.orc_length_score.argtypes = [C.c_int]

@@ -1,0 +1,119 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header declares,
+refuses to run without a GPU (no fallback), and its host-only helpers (packer, Phred tables,
+synthetic generators) behave. No compute call needs a device here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from filtlong_b200 import api, capi
+from oracle import oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "filtlong_b200.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    declared = header_symbols()
+    assert len(declared) >= 40
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(l.split()[-1] for l in out.splitlines() if l.strip())
+    for s in declared:
+        assert s in exported, "header declares %s but the library does not export it" % s
+        assert hasattr(L, s)
+    assert sorted(n for n, _, _ in capi.SYMBOLS) == declared, "capi.SYMBOLS out of sync with the header"
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.FLError) as e:
+        api.Context()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "filtlong_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+                assert "oracle/" not in txt.replace("see oracle for derivation", ""), f
+
+
+def test_packer_layout():
+    seq = b"ACGTNacgtRYGGTTAACCGGTTACGTACGTAAGGCCTTA"    # 40 bases incl. non-ACGT
+    qual = bytes(range(40, 80))
+    hb = api.HostBatch([seq, b"TTTT"], [qual, b"IIII"], want_seq=True, want_nmask=True)
+    assert list(hb.off) == [0, 64] and hb.padded_bases == 128
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    for i, ch in enumerate(seq.upper()):
+        got = (int(hb.seq2b[i >> 4]) >> (30 - 2 * (i & 15))) & 3
+        assert got == code.get(ch, 0)
+        assert ((int(hb.nmask[i >> 5]) >> (i & 31)) & 1) == (0 if ch in code else 1)
+    assert bytes(hb.qual[:40]) == qual and bytes(hb.qual[64:68]) == b"IIII"
+    # the first word is directly the reference's forward 16-mer of the first 16 bases (kmers.cpp:222-229)
+    L = orc.lib()
+    k = 0
+    for ch in seq[:16]:
+        k = ((k << 2) | L.orc_base_fwd(bytes([ch]))) & 0xFFFFFFFF
+    assert int(hb.seq2b[0]) == k
+
+
+def test_phred_tables_match_reference_formula():
+    q = np.zeros(256)
+    a = np.zeros(256)
+    capi.lib().fl_phred_luts(250, capi.ptr(q), capi.ptr(a))
+    L = orc.lib()
+    for b in range(256):
+        ref = L.orc_qscore_to_quality(bytes([b]))
+        assert (q[b] == ref) or (np.isnan(q[b]) and np.isnan(ref))
+        assert a[b] == ref / 250 or (np.isinf(ref))
+
+
+def test_synth_generators_are_deterministic_and_sane():
+    L = capi.lib()
+    n = 50
+    length = np.full(n, 3000, dtype=np.int32)
+    off = (np.arange(n, dtype=np.uint64) * 3008)
+    qbar = np.full(n, 14, dtype=np.uint8)
+    q1 = np.zeros(n * 3008, dtype=np.uint8)
+    q2 = np.zeros_like(q1)
+    L.fl_synth_qual_host(1, n, capi.ptr(off), capi.ptr(length), capi.ptr(qbar), 0, capi.ptr(q1))
+    L.fl_synth_qual_host(1, n, capi.ptr(off), capi.ptr(length), capi.ptr(qbar), 0, capi.ptr(q2))
+    assert np.array_equal(q1, q2)
+    vals = q1.reshape(n, 3008)[:, :3000].astype(int) - 33
+    assert vals.min() >= 1 and vals.max() <= 50
+    assert abs(vals.mean() - 14) < 0.2 and 3.5 < vals.std() < 4.5
+    g = np.zeros(1000 // 16 + 1, dtype=np.uint32)
+    L.fl_synth_genome_host(2, 1000, capi.ptr(g))
+    codes = [(int(g[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(1000)]
+    assert sorted(set(codes)) == [0, 1, 2, 3]
+    # a read with no errors on the forward strand reproduces the genome slice
+    d = capi.SynthReads()
+    rl = np.array([200], dtype=np.int32); ro = np.array([0], dtype=np.uint64)
+    st = np.array([100], dtype=np.uint64); sd = np.array([0], dtype=np.uint8); er = np.array([0], dtype=np.uint32)
+    jp = np.array([0], dtype=np.int32); jl = np.array([0], dtype=np.int32)
+    d.n = 1; d.genome_bases = 1000
+    d.off, d.len, d.start, d.strand, d.err_ppm, d.junk_pos, d.junk_len = map(capi.ptr, (ro, rl, st, sd, er, jp, jl))
+    out = np.zeros(256 // 16, dtype=np.uint32)
+    L.fl_synth_reads_host(3, capi.ptr(g), C.byref(d), 0, capi.ptr(out))
+    rc = [(int(out[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(200)]
+    assert rc == codes[100:300]
+    sd[0] = 1
+    out[:] = 0
+    L.fl_synth_reads_host(3, capi.ptr(g), C.byref(d), 0, capi.ptr(out))
+    rc = [(int(out[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(200)]
+    assert rc == [3 - c for c in codes[100:300]][::-1]

@@ -1,0 +1,229 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs. Per-read values (raw mean / window quality, first/last base, bad and child ranges, hard
+pass flags) must be bit-identical; normalised / final scores within 1e-5 relative (north star);
+selected row IDs identical (modulo the tie class at the cut-off, tests/parity.py)."""
+import numpy as np
+import pytest
+
+from filtlong_b200 import api
+from oracle import oracle as orc
+from tests import parity, util
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(reads, opts, assembly=None, short=None):
+    p, op = api.make_params(**opts), orc.make_params(**opts)
+    ok = None
+    if assembly or short:
+        ok = orc.Kmers()
+        if assembly:
+            ok.add_assembly(assembly)
+        for f in short or []:
+            ok.add_short_reads(f)
+    sc = orc.finalize(orc.score(reads, op, ok), op)
+    ctx, summ = api.score_and_filter(reads, p, assembly=assembly, short_reads=short)
+    return ctx, summ, sc, ok
+
+
+def full_check(ctx, summ, sc):
+    rr, rw = ctx.read_results(), ctx.row_results()
+    parity.check_reads_vs_oracle(rr, sc)
+    parity.check_rows_vs_oracle(rw, rr, sc, summ)
+
+
+PHRED_CASES = [
+    (1, dict(target_bases=400000)),
+    (2, dict(keep_percent=70.0, min_length=500)),
+    (3, dict(keep_percent=85.0, min_mean_q=80.0, window_size=100)),
+    (4, dict(target_bases=250000, length_weight=2.0, mean_q_weight=0.5, window_q_weight=3.0)),
+    (5, dict(min_length=1, keep_percent=90.0, window_size=16)),
+    (6, dict(min_length=1, keep_percent=50.0, window_size=1)),
+    (7, dict(min_window_q=85.0, max_length=6000, window_size=251)),
+    (8, dict(target_bases=10 ** 12)),                 # "not enough reads to reach target"
+    (9, dict(target_bases=1000, min_length=100000)),  # "reads already fall below target"
+]
+
+
+@pytest.mark.parametrize("seed,opts", PHRED_CASES)
+def test_phred_random(seed, opts):
+    rng = np.random.default_rng(seed)
+    genome = util.rand_seq(rng, 50000)
+    reads = [(s, q) for _, s, q in util.long_reads(rng, genome, 300, max_len=12000)]
+    reads.append((b"ACGTACGTAC", b"IIIIIIIIII"))
+    reads.append((util.rand_seq(rng, 300), bytes(rng.integers(33, 127, size=300).astype(np.uint8))))
+    reads.append((util.rand_seq(rng, 251), b"5" * 251))
+    reads.append((util.rand_seq(rng, 250), b"+" * 250))
+    reads.append((util.rand_seq(rng, 1), b"#"))
+    # bytes outside the printable range exercise the signed-char indexing of read.cpp:271
+    reads.append((util.rand_seq(rng, 400), bytes(rng.integers(0, 256, size=400).astype(np.uint8).clip(1, 255))))
+    ctx, summ, sc, _ = run_both(reads, opts)
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def test_phred_long_reads_and_batches():
+    """Reads up to 300 kb, pushed as several batches: results must not depend on batching."""
+    rng = np.random.default_rng(42)
+    reads = []
+    for L in [300000, 150001, 99999, 65536, 4097, 4096, 4095, 17, 16, 15, 2]:
+        reads.append((util.rand_seq(rng, L), util.rand_qual(rng, L, mean_q=rng.uniform(6, 28))))
+    opts = dict(keep_percent=60.0)
+    p, op = api.make_params(**opts), orc.make_params(**opts)
+    sc = orc.finalize(orc.score(reads, op, None), op)
+    ctx = api.Context(p)
+    total = 0
+    for i in range(0, len(reads), 4):
+        hb = api.HostBatch([r[0] for r in reads[i:i + 4]], [r[1] for r in reads[i:i + 4]], want_seq=False)
+        ctx.push(hb)
+        total += hb.total_bases
+    summ = ctx.finalize(-1)
+    assert summ.total_bases == total
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def make_kmer_case(seed, n_reads=150, genome_len=60000, max_len=9000):
+    rng = np.random.default_rng(seed)
+    genome = util.rand_seq(rng, genome_len)
+    ga = np.frombuffer(genome, dtype=np.uint8).copy()
+    ga[1000:1005] = ord("N")
+    ga[20000] = ord("R")
+    genome_n = ga.tobytes()
+    reads = [(s, q) for _, s, q in util.long_reads(rng, genome, n_reads, max_len=max_len)]
+    reads.append((genome[200:215], b"I" * 15))
+    reads.append((genome[300:316], b"I" * 16))
+    reads.append((util.rand_seq(rng, 700), b"5" * 700))
+    reads.append((genome[5000:5400].lower(), b"5" * 400))
+    one_n = bytearray(genome[7000:7400]); one_n[200] = ord("N")
+    reads.append((bytes(one_n), b"5" * 400))
+    reads.append((util.rand_seq(rng, 100) + genome[9000:9400] + util.rand_seq(rng, 30), b"5" * 530))
+    reads.append((util.rand_seq(rng, 10) + genome[11000:11200] + util.rand_seq(rng, 60) + genome[12000:12200], b"5" * 470))
+    return rng, genome, genome_n, reads
+
+
+KMER_CASES = [
+    (11, dict(keep_percent=90.0)),
+    (12, dict(keep_percent=80.0, trim=True, split=100)),
+    (13, dict(target_bases=300000, split=30)),
+    (14, dict(trim=True)),
+    (15, dict(keep_percent=90.0, trim=True, split=250, min_window_q=50.0)),
+    (16, dict(min_length=1000, min_mean_q=60.0, window_size=50, split=16)),
+    (17, dict(keep_percent=75.0, trim=True, split=1, window_size=20)),
+    (18, dict(min_window_q=80.0, split=50, trim=True)),
+]
+
+
+@pytest.mark.parametrize("seed,opts", KMER_CASES)
+def test_kmer_assembly_random(seed, opts):
+    rng, genome, genome_n, reads = make_kmer_case(seed)
+    assembly = [genome_n[:30000], genome_n[30000:], b"ACGT"]
+    ctx, summ, sc, ok = run_both(reads, opts, assembly=assembly)
+    assert ctx.kmers_count() == len(ok)
+    assert np.array_equal(ctx.kmers_export(), ok.dump())
+    probe = np.concatenate([ok.dump()[:500], rng.integers(0, 2 ** 32, size=500, dtype=np.uint64).astype(np.uint32)])
+    assert list(ctx.kmers_contains(probe)) == [int(k) in ok for k in probe]
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,opts", [(21, dict(keep_percent=85.0, trim=True, split=120)),
+                                       (22, dict(target_bases=200000))])
+def test_kmer_short_reads_random(seed, opts):
+    rng, genome, genome_n, reads = make_kmer_case(seed, n_reads=80, genome_len=30000, max_len=5000)
+    r1, r2 = util.short_reads(rng, genome, 5000)
+    short = [[r[1] for r in r1] + [b"ACGTACG", b"N" * 40], [r[1] for r in r2]]
+    ctx, summ, sc, ok = run_both(reads, opts, short=short)
+    assert ctx.kmers_count() == len(ok)
+    assert np.array_equal(ctx.kmers_export(), ok.dump())
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def test_kmer_assembly_then_short_reads():
+    """-a and -1/-2 together: assembly k-mers are in the set first and are skipped by the
+    multiple-copy rule (kmers.cpp:144-145, main.cpp:55-58)."""
+    rng, genome, genome_n, reads = make_kmer_case(31, n_reads=60, genome_len=30000, max_len=4000)
+    r1, r2 = util.short_reads(rng, genome, 3000)
+    asm = [genome_n[:12000]]
+    short = [[r[1] for r in r1], [r[1] for r in r2]]
+    ctx, summ, sc, ok = run_both(reads, dict(keep_percent=80.0, trim=True, split=60), assembly=asm, short=short)
+    assert np.array_equal(ctx.kmers_export(), ok.dump())
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def test_empty_kmer_set_falls_back_to_phred_mode():
+    """H5: the mode is decided by kmers.empty(), not by flags (read.cpp:35, main.cpp:103)."""
+    rng = np.random.default_rng(5)
+    reads = [(util.rand_seq(rng, 500), util.rand_qual(rng, 500)) for _ in range(20)]
+    ctx, summ, sc, ok = run_both(reads, dict(keep_percent=50.0), assembly=[b"ACGTACGTACG"])   # < 16 bp: no k-mers
+    assert ctx.kmers_count() == 0 and len(ok) == 0
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def test_all_identical_reads_give_nan_scores():
+    """H3: stdev == 0 -> every normalised quality and final score is NaN; selection then keeps
+    rows in file order."""
+    seq = b"ACGT" * 100
+    reads = [(seq, b"5" * 400) for _ in range(6)]
+    ctx, summ, sc, _ = run_both(reads, dict(target_bases=1000))
+    rw = ctx.row_results()
+    assert all(np.isnan(rw["final_score"]))
+    full_check(ctx, summ, sc)
+    assert [int(x) for x in rw["passed_final"]] == [1, 1, 1, 0, 0, 0]
+    ctx.close()
+
+
+def test_fasta_without_reference_is_rejected():
+    ctx = api.Context(api.make_params(min_length=1))
+    hb = api.HostBatch([b"ACGT" * 10], None)
+    with pytest.raises(api.FLError) as e:
+        ctx.push(hb)
+    assert "FASTA input not supported without an external reference" in str(e.value)   # main.cpp:104
+    ctx.close()
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", ["phred", "assembly", "short"])
+def test_against_the_real_reference_harness(mode, tmp_path):
+    """Same inputs through the UNMODIFIED reference objects (oracle/_ref/refdump) and the CUDA path."""
+    rng, genome, genome_n, reads = make_kmer_case(77, n_reads=120)
+    named = [("r%d" % i, s, q) for i, (s, q) in enumerate(reads)]
+    fq = util.write_fastq(tmp_path / "reads.fastq", named)
+    opts = dict(keep_percent=80.0) if mode == "phred" else dict(keep_percent=80.0, trim=True, split=90)
+    p = api.make_params(**opts)
+    cli = orc.params_to_cli(orc.make_params(**opts))
+    asm = short = None
+    if mode == "assembly":
+        fa = util.write_fasta(tmp_path / "asm.fasta", [("c1", genome_n)], width=80)
+        cli += ["-a", fa]
+        asm = [genome_n]
+    elif mode == "short":
+        r1, r2 = util.short_reads(rng, genome, 8000)
+        cli += ["-1", util.write_fastq(tmp_path / "s1.fastq", r1), "-2", util.write_fastq(tmp_path / "s2.fastq", r2)]
+        short = [[r[1] for r in r1], [r[1] for r in r2]]
+    ref = orc.run_refdump(cli + [fq])
+    ctx, summ = api.score_and_filter(reads, p, assembly=asm, short_reads=short)
+    if mode != "phred":
+        assert ctx.kmers_count() == ref["n_kmers"]
+    rr, rw = ctx.read_results(), ctx.row_results()
+    row = 0
+    for i, r in enumerate(ref["reads"]):
+        assert parity.same(rr["mean_q"][i], r["mean_q"]) and parity.same(rr["window_q"][i], r["window_q"])
+        assert (rr["first_base_in_kmer"][i], rr["last_base_in_kmer"][i]) == (r["first"], r["last"])
+        assert rr["n_bad"][i] == r["n_bad"] and rr["n_child"][i] == r["n_child"]
+        for c in r["children"]:
+            assert (rw["start"][row], rw["end"][row]) == (c["start"], c["end"])
+            assert parity.same(rw["mean_q"][row], c["mean_q"]) and parity.same(rw["window_q"][row], c["window_q"])
+            row += 1
+        if not r["children"]:
+            row += 1
+    assert row == len(ref["rows"]) == len(rw["parent"])
+    for i, fr in enumerate(ref["rows"]):
+        assert parity.close(rw["final_score"][i], fr["final_score"])
+    parity.check_selection([int(x) for x in rw["passed_final"]], [fr["passed_final"] for fr in ref["rows"]],
+                           [fr["final_score"] for fr in ref["rows"]], [fr["length"] for fr in ref["rows"]])
+    assert summ.keeping == ref["tail"]["keeping"] and summ.target == ref["tail"]["target"]
+    ctx.close()
