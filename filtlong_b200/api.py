@@ -94,6 +94,19 @@ class Context:
     def launch_count(self):
         return int(self.L.fl_ctx_launch_count(self.h))
 
+    KERNELS = {"score_phred": 0, "probe_paint": 1, "kmer_stats": 2, "kmers_add": 3}
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.fl_ctx_enable_timing(self.h, int(on)), "fl_ctx_enable_timing")
+
+    def reset_timing(self):
+        self._ck(self.L.fl_ctx_reset_timing(self.h), "fl_ctx_reset_timing")
+
+    def kernel_time(self, name):
+        ms, n = C.c_double(), C.c_uint64()
+        self._ck(self.L.fl_ctx_kernel_time(self.h, self.KERNELS[name], C.byref(ms), C.byref(n)), "fl_ctx_kernel_time")
+        return ms.value, n.value
+
     # ---- Kmers (kmers.h:28-55) ----
     def kmers_add(self, seqs, multiple_copies, chunk=200000):
         for i in range(0, len(seqs), chunk):

@@ -106,6 +106,9 @@ SYMBOLS = [
     ("fl_ctx_sync", C.c_int, [_P]),
     ("fl_ctx_set_params", C.c_int, [_P, C.POINTER(Params)]),
     ("fl_ctx_launch_count", C.c_uint64, [_P]),
+    ("fl_ctx_enable_timing", C.c_int, [_P, C.c_int]),
+    ("fl_ctx_reset_timing", C.c_int, [_P]),
+    ("fl_ctx_kernel_time", C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     ("fl_padded_len", C.c_uint64, [C.c_int64]),
     ("fl_pack_sequence", None, [C.c_char_p, C.c_char_p, C.c_int64, C.c_uint64, _P, _P, _P]),
     ("fl_kmers_add_batch", C.c_int, [_P, C.POINTER(Batch), C.c_int]),
@@ -133,6 +136,7 @@ SYMBOLS = [
     ("fl_results_reads", C.c_int, [_P, C.POINTER(ReadResults)]),
     ("fl_results_rows", C.c_int, [_P, C.POINTER(RowResults)]),
     ("fl_results_pass_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("fl_results_pass", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("fl_synth_qual_device", C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64, _P]),
     ("fl_synth_qual_host", None, [C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64, _P]),
     ("fl_synth_genome_device", C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),

@@ -5,6 +5,7 @@
 #include "fl_internal.cuh"
 
 static std::string g_create_error;
+static void drain_timers(fl_ctx *c);
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -60,6 +61,7 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    drain_timers(c);
     if (c->d_bitmap) cudaFree(c->d_bitmap);
     for (int i = 0; i < 4; ++i) if (c->d_seen[i]) cudaFree(c->d_seen[i]);
     if (c->d_tfirst) cudaFree(c->d_tfirst);
@@ -95,6 +97,42 @@ extern "C" int fl_ctx_set_params(fl_ctx *c, const fl_params *p) {
 }
 
 extern "C" uint64_t fl_ctx_launch_count(const fl_ctx *c) { return c ? c->launches : 0; }
+
+static void drain_timers(fl_ctx *c) {
+    for (auto &t : c->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            c->kernel_ms[t.which] += ms;
+            c->kernel_launches[t.which]++;
+        }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    c->timed.clear();
+}
+
+extern "C" int fl_ctx_enable_timing(fl_ctx *c, int on) {
+    if (!c) return FL_EINVAL;
+    c->timing = on != 0;
+    return FL_OK;
+}
+
+extern "C" int fl_ctx_reset_timing(fl_ctx *c) {
+    if (!c) return FL_EINVAL;
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    for (int i = 0; i < FL_KERNEL_COUNT; ++i) { c->kernel_ms[i] = 0; c->kernel_launches[i] = 0; }
+    return FL_OK;
+}
+
+extern "C" int fl_ctx_kernel_time(fl_ctx *c, int which, double *total_ms, uint64_t *launches) {
+    if (!c || which < 0 || which >= FL_KERNEL_COUNT) return FL_EINVAL;
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
+    drain_timers(c);
+    if (total_ms) *total_ms = c->kernel_ms[which];
+    if (launches) *launches = c->kernel_launches[which];
+    return FL_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // host packer
@@ -331,6 +369,15 @@ extern "C" int fl_results_pass_dev(fl_ctx *c, void **dev_passed_final, uint64_t 
     if (!c || !dev_passed_final) return FL_EINVAL;
     *dev_passed_final = c->finalized ? (void *)c->w_pfinal.p : (void *)c->w_passed.p;
     if (n_rows) *n_rows = c->n_rows;
+    return FL_OK;
+}
+
+extern "C" int fl_results_pass(fl_ctx *c, uint8_t *host_out, uint64_t cap, uint64_t *n_rows) {
+    if (!c || (!host_out && cap)) return FL_EINVAL;
+    if (n_rows) *n_rows = c->n_rows;
+    size_t n = c->n_rows < cap ? c->n_rows : cap;
+    if (n) FL_CUDA(c, cudaMemcpyAsync(host_out, c->finalized ? c->w_pfinal.p : c->w_passed.p, n, cudaMemcpyDeviceToHost, c->stream));
+    FL_CUDA(c, cudaStreamSynchronize(c->stream));
     return FL_OK;
 }
 

@@ -153,7 +153,32 @@ struct fl_ctx {
     unsigned long long *d_hist = nullptr;  // 256 bins + tie/keeping scalars
     DevVec<double> sc_f64;
 
+    // ---- optional per-kernel timing (fl_ctx_enable_timing) ----
+    bool timing = false;
+    struct TimedLaunch { cudaEvent_t a, b; int which; };
+    std::vector<TimedLaunch> timed;
+    double kernel_ms[FL_KERNEL_COUNT] = {0, 0, 0, 0};
+    uint64_t kernel_launches[FL_KERNEL_COUNT] = {0, 0, 0, 0};
+
     void set_error(const std::string &m) { err = m; }
+};
+
+// RAII bracket: records CUDA events on the launching stream around one kernel launch
+struct KernelTimer {
+    fl_ctx *c;
+    fl_ctx::TimedLaunch t{};
+    bool on;
+    KernelTimer(fl_ctx *ctx, int which) : c(ctx), on(ctx->timing) {
+        if (!on) return;
+        t.which = which;
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(t.a, c->stream);
+    }
+    ~KernelTimer() {
+        if (!on) return;
+        cudaEventRecord(t.b, c->stream);
+        c->timed.push_back(t);
+    }
 };
 
 static inline unsigned fl_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }

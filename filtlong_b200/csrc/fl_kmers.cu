@@ -243,8 +243,11 @@ int fl_kmers_add_view(fl_ctx *ctx, const BatchView &b, int multi) {
     unsigned blocks = (unsigned)((warps_needed + 7) / 8);
     unsigned max_blocks = (unsigned)ctx->sm_count * 8;
     if (blocks > max_blocks) blocks = max_blocks;
-    if (multi) k_kmers_add<true><<<blocks, 256, 0, ctx->stream>>>(a);
-    else k_kmers_add<false><<<blocks, 256, 0, ctx->stream>>>(a);
+    {
+        KernelTimer kt(ctx, FL_KERNEL_KMERS_ADD);
+        if (multi) k_kmers_add<true><<<blocks, 256, 0, ctx->stream>>>(a);
+        else k_kmers_add<false><<<blocks, 256, 0, ctx->stream>>>(a);
+    }
     ctx->launches++;
     FL_CUDA(ctx, cudaGetLastError());
     if (multi) {

@@ -599,7 +599,10 @@ static int score_phred(fl_ctx *ctx, const BatchView &b) {
     unsigned blocks = fl_blocks(n, PHRED_THREADS);
     unsigned max_blocks = (unsigned)ctx->sm_count * 3;
     if (blocks > max_blocks) blocks = max_blocks;
-    k_score_phred<<<blocks, PHRED_THREADS, PHRED_SMEM, ctx->stream>>>(a);
+    {
+        KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
+        k_score_phred<<<blocks, PHRED_THREADS, PHRED_SMEM, ctx->stream>>>(a);
+    }
     ctx->launches++;
     FL_CUDA(ctx, cudaGetLastError());
     ctx->n_reads += n;
@@ -629,7 +632,10 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         unsigned blocks = (unsigned)((n_tiles + 7) / 8);
         unsigned max_blocks = (unsigned)ctx->sm_count * 4;
         if (blocks > max_blocks) blocks = max_blocks;
-        k_probe_paint<<<blocks, 256, 0, st>>>(pa);
+        {
+            KernelTimer kt(ctx, FL_KERNEL_PROBE_PAINT);
+            k_probe_paint<<<blocks, 256, 0, st>>>(pa);
+        }
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
     }
@@ -665,7 +671,10 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         sa.read_base = rb;
         unsigned blocks = fl_blocks(n, 256);
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
-        k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        {
+            KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
+            k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        }
         ctx->launches++;
     }
     // ---- rows ----
@@ -707,7 +716,10 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         sa.r_passed = ctx->r_passed.p + rb;
         unsigned blocks = fl_blocks(n_rows_batch, 256);
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
-        k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        {
+            KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
+            k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+        }
         ctx->launches++;
     }
     FL_CUDA(ctx, cudaGetLastError());

@@ -89,6 +89,14 @@ int fl_ctx_sync(fl_ctx *ctx);
 int fl_ctx_set_params(fl_ctx *ctx, const fl_params *params);
 /* Kernel launches issued by this context so far (for the bench's gpu_launches claim). */
 uint64_t fl_ctx_launch_count(const fl_ctx *ctx);
+/* Optional per-kernel device timing: when enabled, the dominant kernels are bracketed with CUDA
+ * events on the launching stream. fl_ctx_kernel_time synchronises and returns the accumulated
+ * milliseconds and launch count of one kernel since the last fl_ctx_reset_timing. */
+enum { FL_KERNEL_SCORE_PHRED = 0, FL_KERNEL_PROBE_PAINT = 1, FL_KERNEL_KMER_STATS = 2, FL_KERNEL_KMERS_ADD = 3,
+       FL_KERNEL_COUNT = 4 };
+int fl_ctx_enable_timing(fl_ctx *ctx, int on);
+int fl_ctx_reset_timing(fl_ctx *ctx);
+int fl_ctx_kernel_time(fl_ctx *ctx, int which, double *total_ms, uint64_t *launches);
 
 /* ---- host-side packer (replaces the char* hand-off of read.h:32 / kmers.cpp:96-121) ------- */
 /* Padded size of a sequence of `len` bases. */
@@ -209,6 +217,9 @@ int fl_results_rows(fl_ctx *ctx, const fl_row_results *host_out);
 /* Device pointer + count of the final per-row pass flags (uint8), for callers that keep
  * everything on the GPU. */
 int fl_results_pass_dev(fl_ctx *ctx, void **dev_passed_final, uint64_t *n_rows);
+/* Copies only the final per-row pass flags to host memory (the per-step result a streaming
+ * caller needs); *n_rows receives the row count, at most cap flags are written. */
+int fl_results_pass(fl_ctx *ctx, uint8_t *host_out, uint64_t cap, uint64_t *n_rows);
 
 /* ---- synthetic workloads (bench / tests only; deterministic, identical on host and device) -- */
 /* Phred+33 quality string for padded arena `off/len`: per-base Q = clip(qbar[i] + z, 1, 50) with z

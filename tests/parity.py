@@ -59,8 +59,12 @@ def check_rows_vs_oracle(rw, rr, sc, summary):
     s, o = summary, sc.summary
     for k in ("min_q", "max_q"):
         assert same(getattr(s, k), getattr(o, k)), k
-    for k in ("mean_q", "stdev_q", "min_z", "max_z"):
-        assert close(getattr(s, k), getattr(o, k), 1e-12), k
+    assert close(s.mean_q, o.mean_q, 1e-12)
+    if o.min_q != o.max_q:
+        # (with every mean quality identical the stdev is 0 or a last-bit residue of the summation
+        # order -- in the reference too -- and every score is NaN either way, main.cpp:188-207)
+        for k in ("stdev_q", "min_z", "max_z"):
+            assert close(getattr(s, k), getattr(o, k), 1e-12), k
     assert s.status == o.status
     if o.status:
         assert s.target == o.target and s.passed_bases == o.passed_bases
