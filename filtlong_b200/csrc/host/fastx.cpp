@@ -1,0 +1,90 @@
+// filtlong_b200/csrc/host/fastx.cpp -- see fastx.h
+#include "fastx.h"
+
+#include <cctype>
+#include <cstring>
+
+FastxReader::FastxReader(const std::string &path) : buf_(new unsigned char[kBuf]) { fp_ = gzopen(path.c_str(), "r"); }
+
+FastxReader::~FastxReader() {
+    if (fp_) gzclose(fp_);
+    delete[] buf_;
+}
+
+int FastxReader::getc() {
+    if (err_) return -3;
+    if (eof_ && begin_ >= end_) return -1;
+    if (begin_ >= end_) {
+        begin_ = 0;
+        end_ = gzread(fp_, buf_, kBuf);
+        if (end_ == 0) { eof_ = true; return -1; }
+        if (end_ < 0) { eof_ = true; err_ = true; end_ = 0; return -3; }
+    }
+    return (int)buf_[begin_++];
+}
+
+bool FastxReader::get_line(std::string &s, bool append) {
+    bool gotany = false;
+    if (!append) s.clear();
+    for (;;) {
+        if (err_) return false;
+        if (begin_ >= end_) {
+            if (eof_) break;
+            begin_ = 0;
+            end_ = gzread(fp_, buf_, kBuf);
+            if (end_ == 0) { eof_ = true; break; }
+            if (end_ < 0) { eof_ = true; err_ = true; end_ = 0; return false; }
+        }
+        const unsigned char *nl = (const unsigned char *)memchr(buf_ + begin_, '\n', end_ - begin_);
+        int i = nl ? (int)(nl - buf_) : end_;
+        gotany = true;
+        s.append((const char *)buf_ + begin_, i - begin_);
+        begin_ = i + 1;
+        if (i < end_) break;   // newline consumed
+    }
+    if (!gotany && eof_) return false;
+    if (s.size() > 1 && s.back() == '\r') s.pop_back();
+    return true;
+}
+
+int64_t FastxReader::next() {
+    int c;
+    if (last_char_ == 0) {
+        while ((c = getc()) >= 0 && c != '>' && c != '@') {}
+        if (c < 0) return c;
+        last_char_ = c;
+    }
+    comment.clear();
+    seq.clear();
+    qual.clear();
+    // name: up to the first whitespace character
+    name.clear();
+    bool got = false;
+    for (;;) {
+        c = getc();
+        if (c < 0) break;
+        got = true;
+        if (isspace(c)) break;
+        name.push_back((char)c);
+    }
+    if (!got) return c == -3 ? -3 : -1;
+    if (c >= 0 && c != '\n') get_line(comment, false);
+    while ((c = getc()) >= 0 && c != '>' && c != '+' && c != '@') {
+        if (c == '\n') continue;
+        seq.push_back((char)c);
+        get_line(seq, true);
+    }
+    if (c == '>' || c == '@') last_char_ = c;
+    is_fastq = (c == '+');
+    if (!is_fastq) {
+        if (c != '>' && c != '@') last_char_ = 0;   // end of file
+        return (int64_t)seq.size();
+    }
+    while ((c = getc()) >= 0 && c != '\n') {}
+    if (c == -1) return -2;
+    while (get_line(qual, true) && qual.size() < seq.size()) {}
+    if (err_) return -3;
+    last_char_ = 0;
+    if (seq.size() != qual.size()) return -2;
+    return (int64_t)seq.size();
+}

@@ -1,0 +1,109 @@
+// filtlong_b200/csrc/host/kmers.cpp -- see kmers.h. Log lines follow reference src/kmers.cpp:50-72.
+#include "kmers.h"
+
+#include <iostream>
+#include <stdexcept>
+
+#include "arena.h"
+#include "fastx.h"
+#include "misc.h"
+
+void Kmers::check(fl_ctx *ctx, int rc, const char *what) {
+    if (rc == FL_OK) return;
+    throw std::runtime_error(std::string(what) + ": " + fl_last_error(ctx));
+}
+
+Kmers::Kmers() : Kmers(0) {}
+
+Kmers::Kmers(int device) {
+    fl_params p{};
+    p.window_size = 250;
+    p.length_weight = p.mean_q_weight = p.window_q_weight = 1.0;
+    int rc = fl_ctx_create(&p, device, &ctx_);
+    if (rc != FL_OK) throw std::runtime_error(std::string("fl_ctx_create: ") + fl_last_error(nullptr));
+}
+
+Kmers::~Kmers() { fl_ctx_destroy(ctx_); }
+
+uint64_t Kmers::size() {
+    uint64_t n = 0;
+    check(ctx_, fl_kmers_finalize(ctx_, &n), "fl_kmers_finalize");
+    return n;
+}
+
+void Kmers::add_read_fastqs(std::vector<std::string> filenames) {
+    std::cerr << "Hashing 16-mers from short reads\n";
+    int sequence_count = 0;
+    for (auto &filename : filenames) sequence_count += add_reference(filename, true);
+    std::cerr << "  " << int_to_string(sequence_count) << " reads, " << int_to_string((long long)size()) << " 16-mers\n\n";
+}
+
+void Kmers::add_assembly_fasta(std::string filename) {
+    std::cerr << "Hashing 16-mers from assembly\n";
+    std::cerr << "  " << filename << "\n";
+    int sequence_count = add_reference(filename, false);
+    std::cerr << "  " << int_to_string(sequence_count) << " " << (sequence_count == 1 ? "contig" : "contigs") << ", "
+              << int_to_string((long long)size()) << " 16-mers\n\n";
+}
+
+int Kmers::add_reference(const std::string &filename, bool multi) {
+    const uint64_t kBatchBases = 256ull << 20;
+    HostArena arena(true, false, true);
+    FastxReader in(filename);
+    int sequence_count = 0;
+    long long base_count = 0;
+    auto flush = [&]() {
+        if (arena.empty()) return;
+        fl_batch b = arena.batch();
+        check(ctx_, fl_kmers_add_batch(ctx_, &b, multi ? 1 : 0), "fl_kmers_add_batch");
+        arena.clear();
+        print_hash_progress(filename, base_count);
+    };
+    while (in.ok() && in.next() >= 0) {           // a parse error silently ends hashing (kmers.cpp:90-94)
+        ++sequence_count;
+        if (in.seq.size() < 16) continue;          // kmers.cpp:99-100
+        base_count += (long long)in.seq.size();
+        arena.add(in.seq.data(), nullptr, (int64_t)in.seq.size());
+        if (arena.padded_bases() >= kBatchBases) flush();
+    }
+    flush();
+    print_hash_progress(filename, base_count);
+    std::cerr << "\n";
+    return sequence_count;
+}
+
+bool Kmers::is_kmer_present(uint32_t kmer) {
+    uint8_t out = 0;
+    check(ctx_, fl_kmers_contains(ctx_, &kmer, 1, &out), "fl_kmers_contains");
+    return out != 0;
+}
+
+uint32_t Kmers::base_to_bits_forward(char base) {          // kmers.cpp:176-196
+    switch (base) {
+        case 'C': case 'c': return 1u;
+        case 'G': case 'g': return 2u;
+        case 'T': case 't': return 3u;
+        default: return 0u;
+    }
+}
+
+uint32_t Kmers::base_to_bits_reverse(char base) {          // kmers.cpp:199-219
+    switch (base) {
+        case 'G': case 'g': return 1u << 30;
+        case 'C': case 'c': return 2u << 30;
+        case 'A': case 'a': return 3u << 30;
+        default: return 0u;
+    }
+}
+
+uint32_t Kmers::starting_kmer_to_bits_forward(char *sequence) {
+    uint32_t kmer = 0;
+    for (int i = 0; i < 16; ++i) kmer = (kmer << 2) | base_to_bits_forward(sequence[i]);
+    return kmer;
+}
+
+uint32_t Kmers::starting_kmer_to_bits_reverse(char *sequence) {
+    uint32_t kmer = 0;
+    for (int i = 0; i < 16; ++i) kmer = (kmer >> 2) | base_to_bits_reverse(sequence[i]);
+    return kmer;
+}

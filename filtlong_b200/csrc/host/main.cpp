@@ -1,0 +1,192 @@
+// filtlong_b200/csrc/host/main.cpp -- the `filtlong` command line on a B200.
+//
+// Same flow, same stderr log and same stdout as the reference's main (reference
+// src/main.cpp:37-321), restructured around batches: records are parsed and packed on the host,
+// scored on the GPU batch by batch (instead of one `new Read` per record, main.cpp:108), and the
+// normalise / sort / threshold block (main.cpp:169-261) is one fl_finalize call. Pass 2 re-reads
+// the input and prints the survivors exactly like main.cpp:263-313.
+#include <zlib.h>
+
+#include <cstdio>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "arguments.h"
+#include "fastx.h"
+#include "kmers.h"
+#include "misc.h"
+#include "read.h"
+
+#define PROGRAM_VERSION "0.3.1"
+
+int main(int argc, char **argv) {
+    Arguments args(argc, argv);
+    if (args.parsing_result == BAD) return 1;
+    else if (args.parsing_result == HELP) return 0;
+    else if (args.parsing_result == VERSION) {
+        std::cout << "Filtlong v" << PROGRAM_VERSION << "\n";
+        return 0;
+    }
+    std::ios::sync_with_stdio(false);
+    std::cerr << "\n";
+    try {
+        Kmers kmers;                                                      // main.cpp:53-59
+        if (args.assembly_set) kmers.add_assembly_fasta(args.assembly);
+        if (!args.short_reads.empty()) kmers.add_read_fastqs(args.short_reads);
+        const bool kmers_empty = kmers.empty();
+
+        // ---- pass 1: parse, pack and score (main.cpp:61-130) ----
+        long long total_bases = 0, last_progress = 0;
+        if (!args.verbose) std::cerr << "Scoring long reads\n";
+        ReadSet reads(&kmers, &args);
+        std::unordered_set<std::string> seen_names;
+        bool any_fasta = false, any_fastq = false;
+        const unsigned long long kBatchBases = 512ull << 20;
+        unsigned long long queued = 0;
+        size_t verbose_done = 0;
+        auto verbose_flush = [&]() {
+            if (!args.verbose) return;
+            reads.download();
+            for (; verbose_done < reads.n_reads(); ++verbose_done) {
+                Read *r = reads.make_read(verbose_done);
+                r->print_verbose_read_info();                             // main.cpp:110-111
+                delete r;
+            }
+        };
+        {
+            FastxReader in(args.input_reads);
+            while (true) {
+                int64_t l64 = in.ok() ? in.next() : -1;
+                int l = (int)l64;                                         // main.cpp:69,77 (int truncation)
+                if (l == -1) break;
+                if (l == -2) {
+                    verbose_flush();
+                    std::cerr << "Error: incorrect FASTQ format for read " << in.name << "\n";
+                    return 1;
+                }
+                if (l == -3) {
+                    std::cerr << "Error reading " << args.input_reads << "\n";
+                    return 1;
+                }
+                total_bases += (long long)in.seq.size();
+                const bool fasta_format = in.qual.empty() && !in.seq.empty();
+                const bool fastq_format = !in.qual.empty() && !in.seq.empty() && in.qual.size() == in.seq.size();
+                any_fasta = any_fasta || fasta_format;
+                any_fastq = any_fastq || fastq_format;
+                if (any_fasta && any_fastq) {
+                    std::cerr << "\n\n" << "Error: could not parse input reads" << "\n";
+                    std::cerr << "  problem occurred at read " << in.name << "\n";
+                    return 1;
+                }
+                if (fasta_format && kmers_empty) {
+                    std::cerr << "\n\n" << "Error: FASTA input not supported without an external reference" << "\n";
+                    return 1;
+                }
+                // Phred mode needs a quality byte per base; an empty record has neither
+                reads.add(in.name, in.seq.data(), in.qual.empty() ? (kmers_empty ? "" : nullptr) : in.qual.data(), (int)in.seq.size());
+                if (!seen_names.insert(in.name).second) {
+                    verbose_flush();
+                    std::cerr << "Error: duplicate read name: " << in.name << "\n";
+                    return 1;
+                }
+                queued += in.seq.size();
+                if (queued >= kBatchBases) {
+                    reads.flush();
+                    queued = 0;
+                    verbose_flush();
+                }
+                if (total_bases - last_progress >= 483611) {
+                    last_progress = total_bases;
+                    if (!args.verbose) print_read_score_progress((long long)reads.n_reads(), total_bases);
+                }
+            }
+        }
+        reads.flush();
+        verbose_flush();
+        if (!args.verbose) print_read_score_progress((long long)reads.n_reads(), total_bases);
+        std::cerr << "\n";
+        const bool fasta_output = any_fasta, fastq_output = any_fastq;
+
+        // ---- normalise, final score, target (main.cpp:136-261), on the GPU ----
+        fl_summary summary = reads.finalize(total_bases);
+        size_t longest_read_name = 0;
+        if (args.verbose)
+            for (size_t row = 0; row < reads.n_rows(); ++row) longest_read_name = std::max(longest_read_name, reads.row_name(row).size());
+        if (args.trim || args.split_set) {
+            if (args.trim && args.split_set) std::cerr << "  after trimming and splitting: ";
+            else if (args.trim) std::cerr << "  after trimming: ";
+            else std::cerr << "  after splitting: ";
+            std::cerr << int_to_string((long long)reads.n_rows()) << " reads (" << int_to_string(summary.rows_bases) << " bp)\n";
+        }
+        std::cerr << "\n";
+        if (args.verbose) {
+            std::cerr << "\n\n" << "Read name" << "\t" << "Length score" << "\t" << "Mean quality score" << "\t"
+                      << "Window quality score" << "\t" << "Final score" << "\n";
+            for (size_t row = 0; row < reads.n_rows(); ++row) {
+                std::string nm = reads.row_name(row);
+                if (longest_read_name > nm.size()) nm += std::string(longest_read_name - nm.size(), ' ');
+                std::cerr << nm << "\t" << double_to_string(reads.row_lscore[row]) << "\t" << double_to_string(reads.row_nmean[row])
+                          << "\t" << double_to_string(reads.row_nwindow[row]) << "\t" << double_to_string(reads.row_final[row]) << "\n";
+            }
+            std::cerr << "\n";
+        }
+        if (args.target_bases_set || args.keep_percent_set) {
+            std::cerr << "Filtering long reads\n";
+            std::cerr << "  target: " << int_to_string(summary.target) << " bp\n";
+            if (summary.status == 1) std::cerr << "  not enough reads to reach target\n";
+            else if (summary.status == 2) std::cerr << "  reads already fall below target after filtering\n";
+            else std::cerr << "  keeping " << int_to_string(summary.keeping) << " bp\n";
+            std::cerr << "\n";
+        }
+
+        // ---- pass 2: output the keepers in input order (main.cpp:263-313) ----
+        std::cerr << "Outputting passed long reads\n";
+        {
+            FastxReader in(args.input_reads);
+            size_t i = 0;
+            std::string out;
+            out.reserve(1 << 20);
+            while (in.ok() && in.next() >= 0 && i < reads.n_reads()) {
+                const size_t rs = (size_t)reads.row_start[i];
+                if (reads.n_child[i] == 0) {
+                    if (reads.row_pfinal[rs]) {
+                        out += fasta_output ? '>' : '@';
+                        out += in.name;
+                        if (!in.comment.empty()) { out += ' '; out += in.comment; }
+                        out += '\n';
+                        out += in.seq;
+                        out += '\n';
+                        if (fastq_output) { out += "+\n"; out += in.qual; out += '\n'; }
+                    }
+                } else {
+                    for (int c = 0; c < reads.n_child[i]; ++c) {
+                        const size_t row = rs + (size_t)c;
+                        if (!reads.row_pfinal[row]) continue;
+                        const int start = reads.row_s[row], length = reads.row_e[row] - reads.row_s[row];
+                        if (length <= 0) continue;
+                        out += fasta_output ? '>' : '@';
+                        out += reads.row_name(row);
+                        if (!in.comment.empty()) { out += ' '; out += in.comment; }
+                        out += '\n';
+                        out.append(in.seq, (size_t)start, (size_t)length);
+                        out += '\n';
+                        if (fastq_output) { out += "+\n"; out.append(in.qual, (size_t)start, (size_t)length); out += '\n'; }
+                    }
+                }
+                if (out.size() >= (1 << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+                ++i;
+            }
+            fwrite(out.data(), 1, out.size(), stdout);
+            fflush(stdout);
+        }
+        std::cerr << "\n";
+    } catch (const std::exception &e) {
+        std::cerr << "\nError: " << e.what() << "\n";
+        return 1;
+    }
+    return 0;
+}
