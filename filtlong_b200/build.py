@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libfiltlong_b200.so")
-SOURCES = ["fl_api.cu", "fl_scan.cu", "fl_kmers.cu", "fl_score.cu", "fl_select.cu"]
+SOURCES = ["fl_api.cu", "fl_scan.cu", "fl_kmers.cu", "fl_score.cu", "fl_phred.cu", "fl_select.cu"]
 HEADERS = ["fl_internal.cuh", "fl_device.cuh", os.path.join("..", "..", "include", "filtlong_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # --fmad=false: the per-read scores must follow the reference's unfused double arithmetic

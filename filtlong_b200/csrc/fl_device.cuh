@@ -76,3 +76,12 @@ __device__ __forceinline__ uint32_t fl_spread16(uint32_t x) {
 __device__ __forceinline__ uint32_t fl_bloom_hash(uint32_t kmer, uint32_t salt) {
     return salt ^ ~((salt << 11) + (kmer ^ (salt >> 5)));
 }
+
+// hard cut-offs on the RAW qualities, read.cpp:65-73 (else-if chain; each test only if its option is set)
+__device__ __forceinline__ uint8_t fl_hard_cutoffs(const fl_params &p, int length, double mean_q, double window_q) {
+    if (p.min_length_set && length < p.min_length) return 0;
+    else if (p.max_length_set && length > p.max_length) return 0;
+    else if (p.min_mean_q_set && mean_q < p.min_mean_q) return 0;
+    else if (p.min_window_q_set && window_q < p.min_window_q) return 0;
+    return 1;
+}

@@ -197,6 +197,11 @@ int fl_kmers_recount(fl_ctx *ctx);
 
 // ---- implemented in fl_score.cu ----
 int fl_score_view(fl_ctx *ctx, const BatchView &b);
+int fl_reserve_reads(fl_ctx *ctx, size_t n_total);
+int fl_reserve_rows(fl_ctx *ctx, size_t n_total);
+
+// ---- implemented in fl_phred.cu ----
+int fl_score_phred(fl_ctx *ctx, const BatchView &b);
 
 // ---- implemented in fl_select.cu ----
 int fl_norm_select_free(fl_ctx *ctx);

@@ -1,0 +1,403 @@
+// filtlong_b200/csrc/fl_phred.cu -- Phred-mode scoring (reference src/read.cpp:35-39, 208-236, 270-273).
+//
+// The reference's mean and window quality are defined by strictly sequential double additions:
+//     sum += q[c_j]                                   (read.cpp:208-213)
+//     w -= a[c_{j-ws}];  w += a[c_j];  min = min(min, w)   (read.cpp:226-232)
+// with q[c] = 1 - 10^(-(c-33)/10) and a[c] = q[c] / window_size. Their low-order bits depend on that
+// order, and hard thresholds (--min_mean_q / --min_window_q) compare them, so we reproduce the
+// order exactly: every chain is walked by ONE thread with IEEE double adds (file built with
+// --fmad=false), q[] / a[] come from 256-entry tables evaluated with the host libm and replicated
+// in shared memory so that each lane owns its banks (conflict-free 16-byte / 8-byte gathers).
+//
+// Work decomposition (what makes this a GPU algorithm rather than 2 M independent CPU loops):
+//   * reads up to PH_LONG bases: one work item, the fused loop (sum and window together);
+//   * longer reads: one item for the mean chain plus one item per PH_SEG-base SEGMENT of the window
+//     chain. A segment needs the exact value of w at its first base. It is obtained WITHOUT running
+//     the chain: while w stays inside one binade [2^e, 2^(e+1)) every add / subtract of a[c] moves
+//     it by exactly rint(a[c] / ulp_e) grid steps (no rounding drift), so
+//         w_P = W_0 + ulp_e * (S(P) - S(ws)),   S(x) = sum of rint(a[c]/ulp_e) over the ws bases before x,
+//     which costs 2*ws look-ups. This is only a PREDICTION: every segment then runs the true
+//     sequential recurrence from its predicted entry, and k_phred_merge accepts a read only if each
+//     segment's exit value equals the next segment's predicted entry bit-for-bit (induction from
+//     the exact first window). A read that fails the check (binade crossing, round-to-even tie) is
+//     re-scored by the plain fused loop. Results are therefore always the reference's bits; the
+//     prediction only buys parallelism (a 1 Mbp read is 60 concurrent segments instead of a 1 M
+//     step serial tail);
+//   * items are issued in descending cost order over a persistent grid.
+#include "fl_device.cuh"
+
+namespace {
+
+#define PH_THREADS 256
+#define PH_SMEM (256 * 8 * 16 + 256 * 16 * 8)   // {q,a} x 8 copies + a x 16 copies = 64 KiB
+#define PH_SEG 16384
+#define PH_LONG (PH_SEG + PH_SEG / 2)
+
+#define ITEM_FUSED 0xFFFFFFFFu
+#define ITEM_MEAN 0xFFFFFFFEu
+
+struct Tab {
+    const double2 *tqa;   // [c*8]  -> {q[c], a[c]}, lane-private 16-byte bank group
+    const double *ta;     // [c*16] -> a[c],         lane-private 8-byte bank pair
+};
+
+struct PhredArgs {
+    const uint8_t *qual;
+    const uint64_t *off;
+    const int32_t *len;
+    uint32_t n;
+    const double *lut;          // [512]
+    fl_params p;
+    // outputs, already offset to this batch's first read / row
+    int32_t *r_len, *r_first, *r_last, *r_nbad, *r_nchild;
+    double *r_mean, *r_window;
+    uint8_t *r_passed;
+    unsigned long long *r_rowstart;
+    uint32_t *w_parent;
+    int32_t *w_start, *w_end;
+    double *w_mean, *w_window;
+    uint8_t *w_passed;
+    unsigned long long read_base, row_base;
+    // work items
+    const unsigned long long *item_start;   // [n+1] exclusive scan of items per read
+    const uint32_t *order;                  // item indices, descending cost
+    const uint2 *items;                     // {read, kind}
+    unsigned long long n_items;
+    double *it_a, *it_b, *it_c;             // per item: MEAN: sum | SEG: entry, exit, best
+    uint32_t *fallback;                     // [0] = count, [1..] = reads to re-score serially
+};
+
+__device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+template <int WI>
+__device__ __forceinline__ void out_words(const uint4 &a, const uint4 &b, unsigned sh, uint32_t ow[4]) {
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ow[k] = __funnelshift_r(c[WI + k], c[WI + k + 1], sh);
+}
+
+template <bool DO_SUM, bool DO_WIN>
+__device__ __forceinline__ void step(unsigned cin, unsigned cout, const Tab &t, double &sum, double &w, double &best) {
+    if (DO_SUM && DO_WIN) {
+        const double2 qa = t.tqa[cin * 8];
+        const double ao = t.ta[cout * 16];
+        sum += qa.x;                 // read.cpp:210-211
+        w -= ao;                     // read.cpp:229
+        w += qa.y;                   // read.cpp:230
+        if (w < best) best = w;      // read.cpp:231-232
+    } else if (DO_SUM) {
+        sum += t.tqa[cin * 8].x;
+    } else {
+        const double ai = t.ta[cin * 16];
+        const double ao = t.ta[cout * 16];
+        w -= ao;
+        w += ai;
+        if (w < best) best = w;
+    }
+}
+
+// Walks bases [jlo, jhi) of one read in order. DO_WIN requires jlo >= ws.
+template <bool DO_SUM, bool DO_WIN>
+__device__ __forceinline__ void chain(const uint8_t *__restrict__ q, int jlo, int jhi, int ws, const Tab &t, double &sum,
+                                      double &w, double &best) {
+    int j = jlo;
+    for (; (j & 15) && j < jhi; ++j) step<DO_SUM, DO_WIN>(q[j], DO_WIN ? q[j - ws] : 0u, t, sum, w, best);
+    if (j + 16 <= jhi) {
+        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        int blk = 0;
+        unsigned sh = 0, wi = 0;
+        uint4 oa = zero, ob = zero;
+        if (DO_WIN) {
+            const int i0 = j - ws;                     // >= 0; (i0 & 15) is the same for every 16-byte step
+            blk = i0 >> 4;
+            sh = ((unsigned)i0 & 3u) * 8u;
+            wi = ((unsigned)i0 & 15u) >> 2;
+            oa = __ldg(qv + blk);
+            ob = __ldg(qv + blk + 1);                  // never beyond the block of base j
+        }
+        uint4 in = __ldg(qv + (j >> 4));
+        while (j + 16 <= jhi) {
+            const bool more = j + 32 <= jhi;
+            // next step's loads are issued before this step's dependent chains (software prefetch)
+            const uint4 in_next = more ? __ldg(qv + (j >> 4) + 1) : zero;
+            const uint4 oc = (DO_WIN && more) ? __ldg(qv + blk + 2) : zero;
+            uint32_t ow[4] = {0u, 0u, 0u, 0u};
+            if (DO_WIN) {
+                switch (wi) {
+                    case 0: out_words<0>(oa, ob, sh, ow); break;
+                    case 1: out_words<1>(oa, ob, sh, ow); break;
+                    case 2: out_words<2>(oa, ob, sh, ow); break;
+                    default: out_words<3>(oa, ob, sh, ow); break;
+                }
+            }
+            const uint32_t iw[4] = {in.x, in.y, in.z, in.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    step<DO_SUM, DO_WIN>(byte_of(iw[k], b), byte_of(ow[k], b), t, sum, w, best);
+            in = in_next;
+            oa = ob;
+            ob = oc;
+            ++blk;
+            j += 16;
+        }
+    }
+    for (; j < jhi; ++j) step<DO_SUM, DO_WIN>(q[j], DO_WIN ? q[j - ws] : 0u, t, sum, w, best);
+}
+
+__device__ __forceinline__ void write_read(const PhredArgs &a, uint32_t r, int L, double mean, double window) {
+    const uint8_t passed = fl_hard_cutoffs(a.p, L, mean, window);
+    a.r_len[r] = L;
+    a.r_mean[r] = mean;
+    a.r_window[r] = window;
+    a.r_passed[r] = passed;
+    a.r_first[r] = -1;                               // read.cpp:75-76 (only set in k-mer mode)
+    a.r_last[r] = -1;
+    a.r_nbad[r] = 0;
+    a.r_nchild[r] = 0;
+    a.r_rowstart[r] = a.row_base + r;
+    a.w_parent[r] = (uint32_t)(a.read_base + r);
+    a.w_start[r] = 0;
+    a.w_end[r] = L;
+    a.w_mean[r] = mean;
+    a.w_window[r] = window;
+    a.w_passed[r] = passed;
+}
+
+__device__ __forceinline__ void finish(const PhredArgs &a, uint32_t r, int L, double sum, double best) {
+    const double wsd = (double)a.p.window_size;
+    if (best < 0.5 / wsd) best = 0.0;                // read.cpp:233-234
+    write_read(a, r, L, 100.0 * sum / (double)L, 100.0 * best);
+}
+
+// the whole read by one thread: read.cpp:208-236 verbatim
+__device__ __forceinline__ void score_fused(const PhredArgs &a, uint32_t r, const Tab &t) {
+    const int L = a.len[r], ws = a.p.window_size;
+    const uint8_t *q = a.qual + a.off[r];
+    double sum = 0.0, w = 0.0, best = 0.0;
+    chain<true, false>(q, 0, L < ws ? L : ws, ws, t, sum, w, best);
+    if (L <= ws) {                                   // read.cpp:217-218
+        const double mean = 100.0 * sum / (double)L;
+        write_read(a, r, L, mean, mean);
+        return;
+    }
+    w = sum / (double)ws;                            // read.cpp:223
+    best = w;
+    chain<true, true>(q, ws, L, ws, t, sum, w, best);
+    finish(a, r, L, sum, best);
+}
+
+__device__ __forceinline__ int n_segments(int L, int ws) { return (L - ws + PH_SEG - 1) / PH_SEG; }
+
+__device__ __forceinline__ unsigned long long items_of(int L, int ws) {
+    if (L <= PH_LONG || L <= ws + PH_SEG) return 1ull;
+    return 1ull + (unsigned long long)n_segments(L, ws);
+}
+
+// one segment of the window chain of a long read, from a predicted entry value
+__device__ __forceinline__ void score_segment(const PhredArgs &a, uint32_t r, int seg, size_t idx, const Tab &t) {
+    const int L = a.len[r], ws = a.p.window_size;
+    const uint8_t *q = a.qual + a.off[r];
+    double sum = 0.0, w = 0.0, best = 0.0;
+    chain<true, false>(q, 0, ws, ws, t, sum, w, best);
+    const double w0 = sum / (double)ws;              // exact first window (read.cpp:220-223)
+    const int P = ws + seg * PH_SEG;
+    const int Pend = (P + PH_SEG < L) ? P + PH_SEG : L;
+    double entry = w0;
+    if (seg > 0) {
+        // prediction: grid steps of w inside the binade of w0 (see the file header)
+        int e = 0;
+        (void)frexp(w0, &e);                         // w0 = m * 2^e, m in [0.5, 1): binade exponent e - 1
+        const double scale = ldexp(1.0, 53 - e);     // 1 / ulp of that binade
+        long long s0 = 0, sp = 0;
+        for (int i = 0; i < ws; ++i) {
+            s0 += __double2ll_rn(t.ta[(unsigned)q[i] * 16] * scale);
+            sp += __double2ll_rn(t.ta[(unsigned)q[P - ws + i] * 16] * scale);
+        }
+        entry = w0 + (double)(sp - s0) / scale;
+    }
+    w = entry;
+    best = __longlong_as_double(0x7FF0000000000000ll);   // +inf: only values produced inside the segment count
+    chain<false, true>(q, P, Pend, ws, t, sum, w, best);
+    a.it_a[idx] = entry;
+    a.it_b[idx] = w;
+    a.it_c[idx] = best;
+}
+
+__device__ __forceinline__ Tab make_tables(const double *lut, unsigned char *smem_raw) {
+    double2 *tqa_all = reinterpret_cast<double2 *>(smem_raw);                       // [256][8]
+    double *ta_all = reinterpret_cast<double *>(smem_raw + 256 * 8 * 16);           // [256][16]
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        const int c = i >> 3;
+        tqa_all[i] = make_double2(lut[c], lut[256 + c]);
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) ta_all[i] = lut[256 + (i >> 4)];
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    Tab t;
+    t.tqa = tqa_all + (lane & 7);
+    t.ta = ta_all + (lane & 15);
+    return t;
+}
+
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_items(PhredArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Tab t = make_tables(a.lut, smem_raw);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n_items; it += T) {
+        const size_t idx = a.order[it];
+        const uint2 item = a.items[idx];
+        const uint32_t r = item.x;
+        if (item.y == ITEM_FUSED) {
+            score_fused(a, r, t);
+        } else if (item.y == ITEM_MEAN) {
+            double sum = 0.0, w = 0.0, best = 0.0;
+            chain<true, false>(a.qual + a.off[r], 0, a.len[r], a.p.window_size, t, sum, w, best);
+            a.it_a[idx] = sum;
+        } else {
+            score_segment(a, r, (int)item.y, idx, t);
+        }
+    }
+}
+
+// long reads: check the chain of segments and combine (see the file header)
+__global__ void __launch_bounds__(256) k_phred_merge(PhredArgs a) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    const size_t base = a.item_start[r];
+    const int n_it = (int)(a.item_start[r + 1] - base);
+    if (n_it <= 1) return;
+    const int L = a.len[r];
+    const double sum = a.it_a[base];
+    double best = a.it_a[base + 1];                  // entry of segment 0 = exact first window
+    bool ok = true;
+    for (int k = 0; k < n_it - 1; ++k) {
+        const size_t i = base + 1 + k;
+        if (k > 0 && __double_as_longlong(a.it_a[i]) != __double_as_longlong(a.it_b[i - 1])) { ok = false; break; }
+        const double b = a.it_c[i];
+        if (b < best) best = b;
+    }
+    if (ok) finish(a, r, L, sum, best);
+    else a.fallback[1 + atomicAdd(a.fallback, 1u)] = r;
+}
+
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_fallback(PhredArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t n = a.fallback[0];
+    if (n == 0) return;
+    const Tab t = make_tables(a.lut, smem_raw);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        score_fused(a, a.fallback[1 + i], t);
+}
+
+__global__ void k_phred_plan(const int32_t *__restrict__ len, uint32_t n, int ws, unsigned long long *__restrict__ n_items) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) n_items[r] = items_of(len[r], ws);
+}
+
+__global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws, const unsigned long long *__restrict__ item_start,
+                             uint2 *__restrict__ items, int32_t *__restrict__ cost) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int L = len[r];
+    const size_t base = item_start[r];
+    const int cnt = (int)items_of(L, ws);
+    if (cnt == 1) {
+        items[base] = make_uint2(r, ITEM_FUSED);
+        cost[base] = L;
+        return;
+    }
+    items[base] = make_uint2(r, ITEM_MEAN);
+    cost[base] = L / 2;                               // one add per base instead of three
+    for (int k = 0; k < cnt - 1; ++k) {
+        items[base + 1 + k] = make_uint2(r, (uint32_t)k);
+        const int P = ws + k * PH_SEG;
+        cost[base + 1 + k] = ((P + PH_SEG < L) ? PH_SEG : L - P) + 2 * ws;
+    }
+}
+
+}  // namespace
+
+static int ensure_lut(fl_ctx *ctx) {
+    if (ctx->d_lut && ctx->lut_window == ctx->p.window_size) return FL_OK;
+    double h[512];
+    fl_phred_luts(ctx->p.window_size, h, h + 256);
+    if (!ctx->d_lut) FL_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(h)));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->lut_window = ctx->p.window_size;
+    return FL_OK;
+}
+
+int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
+    if (!b.qual) {
+        ctx->set_error("FASTA input not supported without an external reference (no quality string and the k-mer set is empty)");
+        return FL_EINVAL;                                   // main.cpp:103-106
+    }
+    FL_TRY(ensure_lut(ctx));
+    const size_t n = b.n;
+    cudaStream_t st = ctx->stream;
+    FL_TRY(fl_reserve_reads(ctx, ctx->n_reads + n));
+    FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
+    const int ws = ctx->p.window_size;
+    // ---- plan: items per read -> exclusive scan -> item table ----
+    FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, st));
+    k_phred_plan<<<fl_blocks(n, 256), 256, 0, st>>>(b.len, b.n, ws, ctx->sc_u64a.p);
+    ctx->launches++;
+    FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64a.p, ctx->sc_u64a.p, n, ctx->d_scalars));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->sc_u64a.p + n, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(ctx, cudaStreamSynchronize(st));
+    const size_t n_items = (size_t)ctx->h_scalars[0];
+    FL_CUDA(ctx, ctx->sc_u64b.reserve(n_items + 1, 0, st));                 // items (uint2 = 8 bytes)
+    FL_CUDA(ctx, ctx->sc_u32a.reserve(n_items + n + 2, 0, st));             // cost [n_items] | fallback [1 + n]
+    FL_CUDA(ctx, ctx->sc_order.reserve(n_items, 0, st));
+    FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n_items + 8, 0, st));
+    uint2 *items = reinterpret_cast<uint2 *>(ctx->sc_u64b.p);
+    int32_t *cost = reinterpret_cast<int32_t *>(ctx->sc_u32a.p);
+    uint32_t *fallback = ctx->sc_u32a.p + n_items;
+    k_phred_fill<<<fl_blocks(n, 256), 256, 0, st>>>(b.len, b.n, ws, ctx->sc_u64a.p, items, cost);
+    ctx->launches++;
+    FL_CUDA(ctx, cudaMemsetAsync(fallback, 0, sizeof(uint32_t), st));
+    FL_TRY(fl_order_by_length(ctx, cost, n_items, ctx->sc_order.p));
+
+    PhredArgs a{};
+    a.qual = b.qual; a.off = b.off; a.len = b.len; a.n = b.n;
+    a.lut = ctx->d_lut; a.p = ctx->p;
+    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+    a.r_len = ctx->r_len.p + rb; a.r_first = ctx->r_first.p + rb; a.r_last = ctx->r_last.p + rb;
+    a.r_nbad = ctx->r_nbad.p + rb; a.r_nchild = ctx->r_nchild.p + rb;
+    a.r_mean = ctx->r_mean.p + rb; a.r_window = ctx->r_window.p + rb; a.r_passed = ctx->r_passed.p + rb;
+    a.r_rowstart = ctx->r_rowstart.p + rb;
+    a.w_parent = ctx->w_parent.p + wb; a.w_start = ctx->w_start.p + wb; a.w_end = ctx->w_end.p + wb;
+    a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
+    a.read_base = rb; a.row_base = wb;
+    a.item_start = ctx->sc_u64a.p; a.order = ctx->sc_order.p; a.items = items; a.n_items = n_items;
+    a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n_items; a.it_c = ctx->sc_f64.p + 2 * n_items;
+    a.fallback = fallback;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_items, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+        FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+        attr_set = true;
+    }
+    unsigned blocks = fl_blocks(n_items, PH_THREADS);
+    const unsigned max_blocks = (unsigned)ctx->sm_count * 3;
+    if (blocks > max_blocks) blocks = max_blocks;
+    {
+        KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
+        k_phred_items<<<blocks, PH_THREADS, PH_SMEM, st>>>(a);
+    }
+    ctx->launches++;
+    if (n_items > n) {
+        k_phred_merge<<<fl_blocks(n, 256), 256, 0, st>>>(a);
+        k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);
+        ctx->launches += 2;
+    }
+    FL_CUDA(ctx, cudaGetLastError());
+    ctx->n_reads += n;
+    ctx->n_rows += n;
+    return FL_OK;
+}

@@ -2,7 +2,7 @@
 //
 // Two modes, chosen by the state of the k-mer set exactly like read.cpp:35 (`kmers->empty()`):
 //
-//  Phred mode (read.cpp:35-39): one THREAD per read walks the quality string in the reference's
+//  Phred mode (read.cpp:35-39) lives in fl_phred.cu: one THREAD per work item walks the quality string in the reference's
 //    own operation order -- sum += q[c] for the mean (read.cpp:208-213), and the incremental
 //    window recurrence w -= a[c_out]; w += a[c_in] (read.cpp:216-236) -- so mean and window
 //    quality come out bit-identical to the reference (their rounding depends on the order of
@@ -28,158 +28,7 @@ namespace {
 // shared scalar helpers (double arithmetic in exactly the reference's order; file is compiled
 // with --fmad=false so nothing is contracted)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double length_score(int length) {          // read.cpp:241-244
-    const double half = 5000.0;
-    return 100.0 * (1.0 + (-half / ((double)length + half)));
-}
 
-__device__ __forceinline__ uint8_t hard_cutoffs(const fl_params &p, int length, double mean_q, double window_q) {
-    if (p.min_length_set && length < p.min_length) return 0;           // read.cpp:65-73 (else-if chain)
-    else if (p.max_length_set && length > p.max_length) return 0;
-    else if (p.min_mean_q_set && mean_q < p.min_mean_q) return 0;
-    else if (p.min_window_q_set && window_q < p.min_window_q) return 0;
-    return 1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Phred mode
-// ---------------------------------------------------------------------------------------------
-struct PhredArgs {
-    const uint8_t *qual;
-    const uint64_t *off;
-    const int32_t *len;
-    const uint32_t *order;
-    uint32_t n;
-    const double *lut;          // [512]
-    fl_params p;
-    // outputs, already offset to this batch's first read / row
-    int32_t *r_len, *r_first, *r_last, *r_nbad, *r_nchild;
-    double *r_mean, *r_window;
-    uint8_t *r_passed;
-    unsigned long long *r_rowstart;
-    uint32_t *w_parent;
-    int32_t *w_start, *w_end;
-    double *w_mean, *w_window;
-    uint8_t *w_passed;
-    unsigned long long read_base, row_base;
-};
-
-#define PHRED_THREADS 256
-#define PHRED_SMEM (256 * 8 * 16 + 256 * 16 * 8)   // {q,a} x 8 copies + a x 16 copies = 64 KiB
-
-__device__ __forceinline__ void phred_step(unsigned cin, unsigned cout, const double2 *tqa, const double *ta,
-                                           double &sum, double &w, double &best) {
-    double2 qa = tqa[cin * 8];
-    double ao = ta[cout * 16];
-    sum += qa.x;                 // read.cpp:210-211
-    w -= ao;                     // read.cpp:229
-    w += qa.y;                   // read.cpp:230
-    if (w < best) best = w;      // read.cpp:231-232
-}
-
-__device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
-
-template <int WI>
-__device__ __forceinline__ void out_words(const uint4 &a, const uint4 &b, unsigned sh, uint32_t ow[4]) {
-    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ow[k] = __funnelshift_r(c[WI + k], c[WI + k + 1], sh);
-}
-
-__global__ void __launch_bounds__(PHRED_THREADS, 3) k_score_phred(PhredArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *tqa_all = reinterpret_cast<double2 *>(smem_raw);                       // [256][8]
-    double *ta_all = reinterpret_cast<double *>(smem_raw + 256 * 8 * 16);           // [256][16]
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-        int c = i >> 3;
-        tqa_all[i] = make_double2(a.lut[c], a.lut[256 + c]);
-    }
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) ta_all[i] = a.lut[256 + (i >> 4)];
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31;
-    const double2 *tqa = tqa_all + (lane & 7);    // lane-private 16-byte bank group
-    const double *ta = ta_all + (lane & 15);      // lane-private 8-byte bank pair
-    const int ws = a.p.window_size;
-    const double wsd = (double)ws;
-
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n; it += T) {
-        const uint32_t r = a.order[it];
-        const int L = a.len[r];
-        const uint8_t *q = a.qual + a.off[r];
-        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
-        double sum = 0.0;
-        const int head = L < ws ? L : ws;
-        int j = 0;
-        // first window: only the running sum (it is both the mean's prefix and the first window's sum)
-        for (; j + 16 <= head; j += 16) {
-            uint4 v = __ldg(qv + (j >> 4));
-            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) sum += tqa[byte_of(wv[k], b) * 8].x;
-        }
-        for (; j < head; ++j) sum += tqa[(unsigned)q[j] * 8].x;
-
-        double mean, window;
-        if (L <= ws) {                                   // read.cpp:217-218
-            mean = 100.0 * sum / (double)L;
-            window = mean;
-        } else {
-            double w = sum / wsd;                        // read.cpp:223
-            double best = w;
-            for (; (j & 15) && j < L; ++j) phred_step(q[j], q[j - ws], tqa, ta, sum, w, best);
-            if (j + 16 <= L) {
-                const int i0 = j - ws;                   // >= 0
-                int blk = i0 >> 4;
-                const unsigned s = (unsigned)(i0 & 15);  // constant for the whole launch
-                const unsigned sh = (s & 3u) * 8u;
-                const unsigned wi = s >> 2;
-                uint4 oa = __ldg(qv + blk);
-                for (; j + 16 <= L; j += 16) {
-                    uint4 in = __ldg(qv + (j >> 4));
-                    uint4 ob = __ldg(qv + blk + 1);
-                    uint32_t ow[4];
-                    switch (wi) {
-                        case 0: out_words<0>(oa, ob, sh, ow); break;
-                        case 1: out_words<1>(oa, ob, sh, ow); break;
-                        case 2: out_words<2>(oa, ob, sh, ow); break;
-                        default: out_words<3>(oa, ob, sh, ow); break;
-                    }
-                    const uint32_t iw[4] = {in.x, in.y, in.z, in.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            phred_step(byte_of(iw[k], b), byte_of(ow[k], b), tqa, ta, sum, w, best);
-                    oa = ob;
-                    ++blk;
-                }
-            }
-            for (; j < L; ++j) phred_step(q[j], q[j - ws], tqa, ta, sum, w, best);
-            if (best < 0.5 / wsd) best = 0.0;            // read.cpp:233-234
-            window = 100.0 * best;
-            mean = 100.0 * sum / (double)L;
-        }
-        const uint8_t passed = hard_cutoffs(a.p, L, mean, window);
-        a.r_len[r] = L;
-        a.r_mean[r] = mean;
-        a.r_window[r] = window;
-        a.r_passed[r] = passed;
-        a.r_first[r] = -1;                               // read.cpp:75-76 (only set in k-mer mode)
-        a.r_last[r] = -1;
-        a.r_nbad[r] = 0;
-        a.r_nchild[r] = 0;
-        a.r_rowstart[r] = a.row_base + r;
-        a.w_parent[r] = (uint32_t)(a.read_base + r);
-        a.w_start[r] = 0;
-        a.w_end[r] = L;
-        a.w_mean[r] = mean;
-        a.w_window[r] = window;
-        a.w_passed[r] = passed;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // k-mer mode, kernel A: probe + paint
@@ -508,7 +357,7 @@ __global__ void __launch_bounds__(256) k_kmer_stats(StatArgs a) {
         kmer_row_stats(m, S, E, a.p.window_size, &mean, &window);
         a.w_mean[row] = mean;
         a.w_window[row] = window;
-        a.w_passed[row] = hard_cutoffs(a.p, E - S, mean, window);
+        a.w_passed[row] = fl_hard_cutoffs(a.p, E - S, mean, window);
     }
 }
 
@@ -531,7 +380,7 @@ cudaError_t grow(DevVec<T> &v, size_t n, size_t keep, cudaStream_t s) { return v
 
 }  // namespace
 
-static int reserve_reads(fl_ctx *c, size_t n_total) {
+int fl_reserve_reads(fl_ctx *c, size_t n_total) {
     size_t k = c->n_reads;
     cudaStream_t s = c->stream;
     FL_CUDA(c, grow(c->r_len, n_total, k, s));
@@ -546,7 +395,7 @@ static int reserve_reads(fl_ctx *c, size_t n_total) {
     return FL_OK;
 }
 
-static int reserve_rows(fl_ctx *c, size_t n_total) {
+int fl_reserve_rows(fl_ctx *c, size_t n_total) {
     size_t k = c->n_rows;
     cudaStream_t s = c->stream;
     FL_CUDA(c, grow(c->w_parent, n_total, k, s));
@@ -558,63 +407,11 @@ static int reserve_rows(fl_ctx *c, size_t n_total) {
     return FL_OK;
 }
 
-static int ensure_lut(fl_ctx *ctx) {
-    if (ctx->d_lut && ctx->lut_window == ctx->p.window_size) return FL_OK;
-    double h[512];
-    fl_phred_luts(ctx->p.window_size, h, h + 256);
-    if (!ctx->d_lut) FL_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(h)));
-    FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->lut_window = ctx->p.window_size;
-    return FL_OK;
-}
-
-static int score_phred(fl_ctx *ctx, const BatchView &b) {
-    if (!b.qual) {
-        ctx->set_error("FASTA input not supported without an external reference (no quality string and the k-mer set is empty)");
-        return FL_EINVAL;                                   // main.cpp:103-106
-    }
-    FL_TRY(ensure_lut(ctx));
-    const size_t n = b.n;
-    FL_TRY(reserve_reads(ctx, ctx->n_reads + n));
-    FL_TRY(reserve_rows(ctx, ctx->n_rows + n));
-    FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, ctx->stream));
-    FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
-    PhredArgs a{};
-    a.qual = b.qual; a.off = b.off; a.len = b.len; a.order = ctx->sc_order.p; a.n = b.n;
-    a.lut = ctx->d_lut; a.p = ctx->p;
-    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
-    a.r_len = ctx->r_len.p + rb; a.r_first = ctx->r_first.p + rb; a.r_last = ctx->r_last.p + rb;
-    a.r_nbad = ctx->r_nbad.p + rb; a.r_nchild = ctx->r_nchild.p + rb;
-    a.r_mean = ctx->r_mean.p + rb; a.r_window = ctx->r_window.p + rb; a.r_passed = ctx->r_passed.p + rb;
-    a.r_rowstart = ctx->r_rowstart.p + rb;
-    a.w_parent = ctx->w_parent.p + wb; a.w_start = ctx->w_start.p + wb; a.w_end = ctx->w_end.p + wb;
-    a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
-    a.read_base = rb; a.row_base = wb;
-    static bool attr_set = false;
-    if (!attr_set) {
-        FL_CUDA(ctx, cudaFuncSetAttribute(k_score_phred, cudaFuncAttributeMaxDynamicSharedMemorySize, PHRED_SMEM));
-        attr_set = true;
-    }
-    unsigned blocks = fl_blocks(n, PHRED_THREADS);
-    unsigned max_blocks = (unsigned)ctx->sm_count * 3;
-    if (blocks > max_blocks) blocks = max_blocks;
-    {
-        KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
-        k_score_phred<<<blocks, PHRED_THREADS, PHRED_SMEM, ctx->stream>>>(a);
-    }
-    ctx->launches++;
-    FL_CUDA(ctx, cudaGetLastError());
-    ctx->n_reads += n;
-    ctx->n_rows += n;
-    return FL_OK;
-}
-
 static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     if (!b.seq2b) { ctx->set_error("k-mer scoring needs seq2b"); return FL_EINVAL; }
     const size_t n = b.n;
     cudaStream_t st = ctx->stream;
-    FL_TRY(reserve_reads(ctx, ctx->n_reads + n));
+    FL_TRY(fl_reserve_reads(ctx, ctx->n_reads + n));
     // ---- kernel A: probe + paint ----
     FL_CUDA(ctx, ctx->sc_mask.reserve((size_t)(b.padded_bases >> 5) + 1, 0, st));
     FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, st));
@@ -686,7 +483,7 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         FL_CUDA(ctx, cudaStreamSynchronize(st));
         n_rows_batch = (size_t)ctx->h_scalars[0];
     }
-    FL_TRY(reserve_rows(ctx, ctx->n_rows + n_rows_batch));
+    FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n_rows_batch));
     if (!may_have_children) {
         k_identity_rows<<<fl_blocks(n, 256), 256, 0, st>>>(b.n, b.len, ctx->w_parent.p + wb, ctx->w_start.p + wb,
                                                           ctx->w_end.p + wb, rb);
@@ -732,6 +529,6 @@ int fl_score_view(fl_ctx *ctx, const BatchView &b) {
     if (b.n == 0) return FL_OK;
     if (ctx->kmers_count_stale || ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
     ctx->finalized = false;
-    if (ctx->n_kmers == 0) return score_phred(ctx, b);     // read.cpp:35: kmers->empty()
+    if (ctx->n_kmers == 0) return fl_score_phred(ctx, b);     // read.cpp:35: kmers->empty()
     return score_kmer(ctx, b);
 }

@@ -83,6 +83,25 @@ def test_phred_long_reads_and_batches():
     ctx.close()
 
 
+@pytest.mark.parametrize("ws", [250, 16, 1000])
+def test_phred_long_read_segment_prediction_and_fallback(ws):
+    """Long reads are cut into segments whose entry value of the window recurrence is PREDICTED and
+    then verified (fl_phred.cu). These reads make the prediction fail on purpose -- the window
+    quality crosses binades (0.99 -> 0.2 -> 0.99), window sizes with round-to-even ties (16), bytes
+    outside the Phred range -- so the serial re-score path must produce the reference's bits too."""
+    rng = np.random.default_rng(99)
+    reads = []
+    reads.append((b"A" * 120000, b"I" * 50000 + b"#" * 30000 + b"I" * 40000))                  # binade crossings
+    reads.append((b"A" * 90000, bytes(rng.integers(33, 43, size=90000).astype(np.uint8))))      # w around 0.3-0.6
+    reads.append((b"A" * 70000, bytes(rng.integers(1, 256, size=70000).astype(np.uint8))))      # garbage bytes
+    reads.append((b"A" * 200000, util.rand_qual(rng, 200000, mean_q=12)))                       # well behaved
+    reads.append((b"A" * 60001, b"!" * 60001))                                                  # Q0: quality 0 everywhere
+    reads.append((b"A" * 45000, b"5" * 45000))                                                  # constant quality
+    ctx, summ, sc, _ = run_both(reads, dict(keep_percent=50.0, window_size=ws))
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
 def make_kmer_case(seed, n_reads=150, genome_len=60000, max_len=9000):
     rng = np.random.default_rng(seed)
     genome = util.rand_seq(rng, genome_len)
