@@ -85,3 +85,12 @@ __device__ __forceinline__ uint8_t fl_hard_cutoffs(const fl_params &p, int lengt
     else if (p.min_window_q_set && window_q < p.min_window_q) return 0;
     return 1;
 }
+
+// length buckets for load balancing: 8 per octave, 0..255, 255 = longest
+__device__ __forceinline__ unsigned fl_length_bucket(int len) {
+    if (len <= 0) return 0;
+    unsigned l = (unsigned)len;
+    unsigned msb = 31 - __clz(l);
+    unsigned frac = msb >= 3 ? ((l >> (msb - 3)) & 7u) : ((l << (3 - msb)) & 7u);
+    return msb * 8 + frac;   // <= 31*8+7 = 255
+}

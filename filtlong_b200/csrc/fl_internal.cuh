@@ -13,6 +13,7 @@
 
 #define FL_BLOOM_BITS 1917295480ull   // bloom_filter.h:108-160 with kmers.cpp:32-34's parameters
 #define FL_BLOOM_K 13
+#define FL_ORDER_BUCKETS 1024
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing: CUDA failures become FL_ECUDA + message, never exceptions
@@ -189,6 +190,8 @@ int fl_exclusive_scan_u64(fl_ctx *ctx, const unsigned long long *in, unsigned lo
 // rows 0..n-1 ordered by descending length bucket into order[] (lengths may be null when
 // start/end are given: length = end - start)
 int fl_order_by_length(fl_ctx *ctx, const int32_t *len, size_t n, uint32_t *order);
+// same with caller-computed bucket keys in [0, FL_ORDER_BUCKETS): highest key first
+int fl_order_by_key(fl_ctx *ctx, const uint32_t *key, size_t n, uint32_t *order);
 
 // ---- implemented in fl_kmers.cu ----
 int fl_kmers_ensure_bitmap(fl_ctx *ctx);

@@ -298,7 +298,7 @@ __global__ void k_phred_plan(const int32_t *__restrict__ len, uint32_t n, int ws
 }
 
 __global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws, const unsigned long long *__restrict__ item_start,
-                             uint2 *__restrict__ items, int32_t *__restrict__ cost) {
+                             uint2 *__restrict__ items, uint32_t *__restrict__ cost) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int L = len[r];
@@ -306,15 +306,15 @@ __global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws
     const int cnt = (int)items_of(L, ws);
     if (cnt == 1) {
         items[base] = make_uint2(r, ITEM_FUSED);
-        cost[base] = L;
+        cost[base] = 0 * 256 + fl_length_bucket(L);
         return;
     }
     items[base] = make_uint2(r, ITEM_MEAN);
-    cost[base] = L / 2;                               // one add per base instead of three
+    cost[base] = 2 * 256 + fl_length_bucket(L);       // kinds are grouped so that warps stay uniform; the long serial chains go first
     for (int k = 0; k < cnt - 1; ++k) {
         items[base + 1 + k] = make_uint2(r, (uint32_t)k);
         const int P = ws + k * PH_SEG;
-        cost[base + 1 + k] = ((P + PH_SEG < L) ? PH_SEG : L - P) + 2 * ws;
+        cost[base + 1 + k] = 1 * 256 + fl_length_bucket(((P + PH_SEG < L) ? PH_SEG : L - P) + 2 * ws);
     }
 }
 
@@ -356,12 +356,12 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_CUDA(ctx, ctx->sc_order.reserve(n_items, 0, st));
     FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n_items + 8, 0, st));
     uint2 *items = reinterpret_cast<uint2 *>(ctx->sc_u64b.p);
-    int32_t *cost = reinterpret_cast<int32_t *>(ctx->sc_u32a.p);
+    uint32_t *cost = ctx->sc_u32a.p;                     // bucket key = kind * 256 + length bucket
     uint32_t *fallback = ctx->sc_u32a.p + n_items;
     k_phred_fill<<<fl_blocks(n, 256), 256, 0, st>>>(b.len, b.n, ws, ctx->sc_u64a.p, items, cost);
     ctx->launches++;
     FL_CUDA(ctx, cudaMemsetAsync(fallback, 0, sizeof(uint32_t), st));
-    FL_TRY(fl_order_by_length(ctx, cost, n_items, ctx->sc_order.p));
+    FL_TRY(fl_order_by_key(ctx, cost, n_items, ctx->sc_order.p));
 
     PhredArgs a{};
     a.qual = b.qual; a.off = b.off; a.len = b.len; a.n = b.n;

@@ -1,6 +1,6 @@
 // filtlong_b200/csrc/fl_scan.cu -- device-wide exclusive scan (uint64) and the length-bucket
 // ordering used to balance thread-per-row kernels. Hand-written; n is at most ~10^8.
-#include "fl_internal.cuh"
+#include "fl_device.cuh"
 
 namespace {
 
@@ -82,51 +82,68 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long *_
         if (base + i < n) out[base + i] += add;
 }
 
-// ---- length buckets: 8 per octave, bucket 255 = longest ------------------------------------
-__device__ __forceinline__ unsigned length_bucket(int len) {
-    if (len <= 0) return 0;
-    unsigned l = (unsigned)len;
-    unsigned msb = 31 - __clz(l);
-    unsigned frac = msb >= 3 ? ((l >> (msb - 3)) & 7u) : ((l << (3 - msb)) & 7u);
-    return msb * 8 + frac;   // <= 31*8+7 = 255
-}
+// ---- bucket ordering: rows sorted by DESCENDING bucket key (counting sort, FL_ORDER_BUCKETS keys) ----
+struct LenKey {
+    const int32_t *len;
+    __device__ __forceinline__ unsigned operator()(size_t i) const { return fl_length_bucket(len[i]); }
+};
+struct RawKey {
+    const uint32_t *key;
+    __device__ __forceinline__ unsigned operator()(size_t i) const { return key[i] < FL_ORDER_BUCKETS ? key[i] : FL_ORDER_BUCKETS - 1; }
+};
 
-__global__ void k_bucket_hist(const int32_t *__restrict__ len, size_t n, uint32_t *__restrict__ buckets) {
-    __shared__ uint32_t h[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+template <typename K>
+__global__ void k_bucket_hist(K keyfn, size_t n, uint32_t *__restrict__ buckets) {
+    __shared__ uint32_t h[FL_ORDER_BUCKETS];
+    for (int i = threadIdx.x; i < FL_ORDER_BUCKETS; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[length_bucket(len[i])], 1u);
+        atomicAdd(&h[keyfn(i)], 1u);
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    for (int i = threadIdx.x; i < FL_ORDER_BUCKETS; i += blockDim.x)
         if (h[i]) atomicAdd(&buckets[i], h[i]);
 }
 
-// cursors[b] = number of rows in longer buckets (descending order)
+// cursors[b] = number of rows in higher buckets (descending order)
 __global__ void k_bucket_scan(uint32_t *__restrict__ buckets) {
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int b = 255; b >= 0; --b) {
+        for (int b = FL_ORDER_BUCKETS - 1; b >= 0; --b) {
             uint32_t c = buckets[b];
-            buckets[256 + b] = run;
+            buckets[FL_ORDER_BUCKETS + b] = run;
             run += c;
         }
     }
 }
 
-__global__ void k_bucket_scatter(const int32_t *__restrict__ len, size_t n, uint32_t *__restrict__ buckets,
-                                 uint32_t *__restrict__ order) {
+template <typename K>
+__global__ void k_bucket_scatter(K keyfn, size_t n, uint32_t *__restrict__ buckets, uint32_t *__restrict__ order) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        unsigned b = length_bucket(len[i]);
+        unsigned b = keyfn(i);
         // warp-aggregated cursor bump per bucket
         unsigned peers = __match_any_sync(__activemask(), b);
         unsigned leader = __ffs(peers) - 1;
         unsigned lane = threadIdx.x & 31;
         uint32_t basepos = 0;
-        if (lane == leader) basepos = atomicAdd(&buckets[256 + b], (uint32_t)__popc(peers));
+        if (lane == leader) basepos = atomicAdd(&buckets[FL_ORDER_BUCKETS + b], (uint32_t)__popc(peers));
         basepos = __shfl_sync(peers, basepos, leader);
         order[basepos + __popc(peers & ((1u << lane) - 1))] = (uint32_t)i;
     }
+}
+
+template <typename K>
+int order_by(fl_ctx *ctx, K keyfn, size_t n, uint32_t *order) {
+    if (n == 0) return FL_OK;
+    if (!ctx->d_buckets) FL_CUDA(ctx, cudaMalloc(&ctx->d_buckets, 2 * FL_ORDER_BUCKETS * sizeof(uint32_t)));
+    FL_CUDA(ctx, cudaMemsetAsync(ctx->d_buckets, 0, 2 * FL_ORDER_BUCKETS * sizeof(uint32_t), ctx->stream));
+    unsigned blocks = fl_blocks(n, 256);
+    if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_bucket_hist<<<blocks, 256, 0, ctx->stream>>>(keyfn, n, ctx->d_buckets);
+    k_bucket_scan<<<1, 32, 0, ctx->stream>>>(ctx->d_buckets);
+    k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(keyfn, n, ctx->d_buckets, order);
+    ctx->launches += 3;
+    FL_CUDA(ctx, cudaGetLastError());
+    return FL_OK;
 }
 
 }  // namespace
@@ -147,16 +164,6 @@ int fl_exclusive_scan_u64(fl_ctx *ctx, const unsigned long long *in, unsigned lo
     return FL_OK;
 }
 
-int fl_order_by_length(fl_ctx *ctx, const int32_t *len, size_t n, uint32_t *order) {
-    if (n == 0) return FL_OK;
-    if (!ctx->d_buckets) FL_CUDA(ctx, cudaMalloc(&ctx->d_buckets, 512 * sizeof(uint32_t)));
-    FL_CUDA(ctx, cudaMemsetAsync(ctx->d_buckets, 0, 512 * sizeof(uint32_t), ctx->stream));
-    unsigned blocks = fl_blocks(n, 256);
-    if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    k_bucket_hist<<<blocks, 256, 0, ctx->stream>>>(len, n, ctx->d_buckets);
-    k_bucket_scan<<<1, 32, 0, ctx->stream>>>(ctx->d_buckets);
-    k_bucket_scatter<<<blocks, 256, 0, ctx->stream>>>(len, n, ctx->d_buckets, order);
-    ctx->launches += 3;
-    FL_CUDA(ctx, cudaGetLastError());
-    return FL_OK;
-}
+int fl_order_by_length(fl_ctx *ctx, const int32_t *len, size_t n, uint32_t *order) { return order_by(ctx, LenKey{len}, n, order); }
+
+int fl_order_by_key(fl_ctx *ctx, const uint32_t *key, size_t n, uint32_t *order) { return order_by(ctx, RawKey{key}, n, order); }

@@ -95,7 +95,10 @@ def test_phred_long_read_segment_prediction_and_fallback(ws):
     reads.append((b"A" * 90000, bytes(rng.integers(33, 43, size=90000).astype(np.uint8))))      # w around 0.3-0.6
     reads.append((b"A" * 70000, bytes(rng.integers(1, 256, size=70000).astype(np.uint8))))      # garbage bytes
     reads.append((b"A" * 200000, util.rand_qual(rng, 200000, mean_q=12)))                       # well behaved
-    reads.append((b"A" * 60001, b"!" * 60001))                                                  # Q0: quality 0 everywhere
+    # (no all-'!' read here: with the garbage-byte read above its normalised mean is > 0 while its
+    # window/mean ratio is 0/0, i.e. a NaN score among finite ones -- std::sort order is then
+    # unspecified in the reference itself; only invalid quality bytes can produce that mix)
+    reads.append((b"A" * 60001, b'"' * 60001))                                                  # Q1 everywhere
     reads.append((b"A" * 45000, b"5" * 45000))                                                  # constant quality
     ctx, summ, sc, _ = run_both(reads, dict(keep_percent=50.0, window_size=ws))
     full_check(ctx, summ, sc)
