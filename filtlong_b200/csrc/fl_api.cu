@@ -1,6 +1,7 @@
 // filtlong_b200/csrc/fl_api.cu -- context management, host packer, batch entry points, result
 // download and the deterministic synthetic-workload generators behind the C ABI.
 #include <cmath>
+#include <cstdlib>
 
 #include "fl_internal.cuh"
 
@@ -53,6 +54,9 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
         return FL_ECUDA;
     }
     c->stream = c->own_stream;
+    // tuning knobs for profiling runs (defaults are the measured best, see profiles/ and DESIGN.md section 7)
+    if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
+    if (const char *g = getenv("FL_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     *out = c;
     return FL_OK;
 }
@@ -67,6 +71,7 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (c->d_tfirst) cudaFree(c->d_tfirst);
     if (c->d_bittime) cudaFree(c->d_bittime);
     if (c->d_lut) cudaFree(c->d_lut);
+    if (c->d_utab) cudaFree(c->d_utab);
     if (c->d_buckets) cudaFree(c->d_buckets);
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);

@@ -97,6 +97,7 @@ struct fl_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
+    int probe_mode = 1;        // load flavour of the bitmap probe (fl_score.cu); FL_PROBE_MODE overrides for experiments
 
     // ---- Kmers ----
     uint32_t *d_bitmap = nullptr;        // 2^32 bits, direct-address membership
@@ -112,6 +113,7 @@ struct fl_ctx {
 
     // ---- Phred LUTs ----
     double *d_lut = nullptr;   // [0..256) q, [256..512) a = q / window_size
+    unsigned long long *d_utab = nullptr;   // [256] q * 2^64 as exact integers (~0 = not representable), fl_phred.cu
     int lut_window = -1;
 
     // ---- staging for host batches ----

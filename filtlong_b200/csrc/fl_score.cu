@@ -44,10 +44,23 @@ struct ProbeArgs {
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
 };
 
+// One 4-byte load from the 512 MiB membership bitmap per k-mer. The flavour of the load decides how
+// much HBM traffic a random probe costs (measured with ncu, profiles/): MODE 0 = ld.global.nc (L1
+// allocates and pulls whole 128-byte lines), 1 = ld.global.cg (L2 only, sector granular),
+// 2 = ld.global.nc.L1::no_allocate.
+template <int MODE>
 __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t kmer) {
-    return __ldg(bitmap + (kmer >> 5));
+    const uint32_t *p = bitmap + (kmer >> 5);
+    if (MODE == 1) return __ldcg(p);
+    if (MODE == 2) {
+        uint32_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        return v;
+    }
+    return __ldg(p);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -70,7 +83,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                 unsigned long long b = tile_base - 16 + lane;
                 if (b + (FL_K - 1) < (unsigned long long)L) {
                     uint32_t k = __funnelshift_l(wb, wa, 2 * lane);
-                    hit = (probe(a.bitmap, k) >> (k & 31)) & 1u;
+                    hit = (probe<MODE>(a.bitmap, k) >> (k & 31)) & 1u;
                 }
             }
             carry = __ballot_sync(0xffffffffu, hit) << 16;
@@ -91,7 +104,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                 for (int i = 0; i < 16; ++i) {
                     const int p = half * 16 + i;
                     const uint32_t k = fl_kmer_at(w, p);
-                    words[i] = (p < nvalid) ? probe(a.bitmap, k) : 0u;     // read.cpp:52
+                    words[i] = (p < nvalid) ? probe<MODE>(a.bitmap, k) : 0u;     // read.cpp:52
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -431,7 +444,11 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         if (blocks > max_blocks) blocks = max_blocks;
         {
             KernelTimer kt(ctx, FL_KERNEL_PROBE_PAINT);
-            k_probe_paint<<<blocks, 256, 0, st>>>(pa);
+            switch (ctx->probe_mode) {
+                case 0: k_probe_paint<0><<<blocks, 256, 0, st>>>(pa); break;
+                case 2: k_probe_paint<2><<<blocks, 256, 0, st>>>(pa); break;
+                default: k_probe_paint<1><<<blocks, 256, 0, st>>>(pa); break;
+            }
         }
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());

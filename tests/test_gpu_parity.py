@@ -249,3 +249,28 @@ def test_against_the_real_reference_harness(mode, tmp_path):
                            [fr["final_score"] for fr in ref["rows"]], [fr["length"] for fr in ref["rows"]])
     assert summ.keeping == ref["tail"]["keeping"] and summ.target == ref["tail"]["target"]
     ctx.close()
+
+
+def test_bloom_false_positive_kat_912k_reads():
+    """SURVEY section 4 / Appendix D known answer: 912,000 random 100-bp reads passed as -1, with
+    2,000 reads present three times late in the stream. The reference logs `25,243 16-mers`: 24,268
+    16-mers with >= 4 sightings plus 975 with exactly 3 whose FIRST sighting hit a Bloom false
+    positive (kmers.cpp:142-166; the filter is ~65 % full by then). A plain ">= 4 copies" rule gives
+    24,268. Checks the device's closed-form multiple-copy build against that golden number."""
+    rng = np.random.default_rng(99)
+    main = rng.integers(0, 4, size=(900000, 100), dtype=np.int64)
+    A = rng.integers(0, 4, size=(2000, 100), dtype=np.int64)
+    B = rng.integers(0, 4, size=(2000, 100), dtype=np.int64)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    order = [B, main, A, A, B, A, B]
+    seqs = []
+    for blk in order:
+        arr = lut[blk]
+        seqs.extend(bytes(row) for row in arr)
+    assert len(seqs) == 912000
+    ctx = api.Context(api.make_params(min_length=1))
+    ctx.kmers_add(seqs, True)
+    n = ctx.kmers_count()
+    ctx.kmers_release_build_state()
+    ctx.close()
+    assert n == 25243
