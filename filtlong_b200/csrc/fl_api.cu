@@ -56,6 +56,19 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     c->stream = c->own_stream;
     // tuning knobs for profiling runs (defaults are the measured best, see profiles/ and DESIGN.md section 7)
     if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
+    if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
+    {
+        const char *pe = getenv("FL_L2_PERSIST");
+        if (!pe || atoi(pe) != 0) {
+            size_t want = (size_t)prop.persistingL2CacheMaxSize;
+            if (want > ((size_t)96 << 20)) want = (size_t)96 << 20;
+            if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                c->l2_persist_bytes = want;
+                c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+            }
+        }
+    }
+    if (const char *f = getenv("FL_FILTER_LOG2_WORDS")) c->filter_log2_words = (unsigned)atoi(f);
     if (const char *g = getenv("FL_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     *out = c;
     return FL_OK;
@@ -67,6 +80,7 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     cudaDeviceSynchronize();
     drain_timers(c);
     if (c->d_bitmap) cudaFree(c->d_bitmap);
+    if (c->d_filter) cudaFree(c->d_filter);
     for (int i = 0; i < 4; ++i) if (c->d_seen[i]) cudaFree(c->d_seen[i]);
     if (c->d_tfirst) cudaFree(c->d_tfirst);
     if (c->d_bittime) cudaFree(c->d_bittime);

@@ -94,3 +94,12 @@ __device__ __forceinline__ unsigned fl_length_bucket(int len) {
     unsigned frac = msb >= 3 ? ((l >> (msb - 3)) & 7u) : ((l << (3 - msb)) & 7u);
     return msb * 8 + frac;   // <= 31*8+7 = 255
 }
+
+// L2-resident pre-filter in front of the 512 MiB bitmap (fl_kmers.cu / fl_score.cu): two bits in ONE
+// 64-bit word of a 2^log2_words-word table. No false negatives, so "filter says absent" is final.
+__device__ __forceinline__ void fl_filter_slot(uint32_t kmer, unsigned log2_words, uint32_t &word, unsigned long long &bits) {
+    const uint32_t h1 = kmer * 0x9E3779B1u;
+    const uint32_t h2 = (kmer ^ (kmer >> 15)) * 0x85EBCA6Bu;
+    word = h1 >> (32 - log2_words);
+    bits = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
+}

@@ -102,6 +102,12 @@ struct fl_ctx {
     // ---- Kmers ----
     uint32_t *d_bitmap = nullptr;        // 2^32 bits, direct-address membership
     uint64_t n_kmers = 0;
+    // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
+    unsigned long long *d_filter = nullptr;
+    unsigned filter_log2_words = 23;     // 2^23 x 8 B = 64 MiB
+    bool use_filter = false;
+    int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
+    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside granted to this context
     bool kmers_count_stale = false;
     // multiple-copy build state (kmers.cpp:142-166 in closed form, see fl_kmers.cu)
     uint32_t *d_seen[4] = {nullptr, nullptr, nullptr, nullptr};   // ">= 1,2,3,4 sightings" bitmaps

@@ -185,6 +185,23 @@ __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ b
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// pre-filter build: every member of the bitmap sets its two filter bits
+__global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict__ bm, unsigned long long *__restrict__ filter,
+                                                      unsigned log2_words) {
+    const size_t n_words = (size_t)1 << 27;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
+        uint32_t bits = bm[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            uint32_t word;
+            unsigned long long fb;
+            fl_filter_slot((uint32_t)(w << 5) | (uint32_t)b, log2_words, word, fb);
+            if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
+        }
+    }
+}
+
 __global__ void k_contains(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ q, uint32_t n,
                            uint8_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +291,18 @@ int fl_kmers_recount(fl_ctx *ctx) {
     FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_kmers = ctx->h_scalars[0];
     ctx->kmers_count_stale = false;
+    // The pre-filter pays off while it stays selective: <= 1 member per 8 filter bits (false-positive
+    // rate of the two-bit test below ~5 %). Larger sets (e.g. a 3 Gbp assembly fills 75 % of the key
+    // space) are probed directly.
+    const size_t filter_words = (size_t)1 << ctx->filter_log2_words;
+    ctx->use_filter = ctx->filter_enabled && ctx->n_kmers > 0 && ctx->n_kmers * 8 <= filter_words * 64;
+    if (ctx->use_filter) {
+        if (!ctx->d_filter) FL_CUDA(ctx, cudaMalloc(&ctx->d_filter, filter_words * sizeof(unsigned long long)));
+        FL_CUDA(ctx, cudaMemsetAsync(ctx->d_filter, 0, filter_words * sizeof(unsigned long long), ctx->stream));
+        k_filter_build<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->d_bitmap, ctx->d_filter, ctx->filter_log2_words);
+        ctx->launches++;
+        FL_CUDA(ctx, cudaGetLastError());
+    }
     return FL_OK;
 }
 

@@ -41,6 +41,8 @@ struct ProbeArgs {
     uint32_t n;
     unsigned long long n_tiles;
     const uint32_t *bitmap;
+    const unsigned long long *filter;        // L2-resident pre-filter (fl_kmers.cu), used when FILT
+    unsigned filter_log2_words;
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
 };
 
@@ -60,7 +62,7 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
     return __ldg(p);
 }
 
-template <int MODE>
+template <int MODE, bool FILT>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -100,11 +102,32 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
+                uint32_t go = 0xFFFFu;                // which of the 16 k-mers still need the exact bitmap
+                if (FILT) {
+                    // 16 independent loads from the 64 MiB pre-filter (kept in L2): most k-mers of a
+                    // noisy read are absent and stop here, without touching HBM
+                    unsigned long long f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t word;
+                        unsigned long long fb;
+                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, word, fb);
+                        f[i] = (half * 16 + i < nvalid) ? __ldg(a.filter + word) : 0ull;
+                    }
+                    go = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t word;
+                        unsigned long long fb;
+                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, word, fb);
+                        go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int p = half * 16 + i;
                     const uint32_t k = fl_kmer_at(w, p);
-                    words[i] = (p < nvalid) ? probe<MODE>(a.bitmap, k) : 0u;     // read.cpp:52
+                    words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(a.bitmap, k) : 0u;     // read.cpp:52
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -439,15 +462,41 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         ProbeArgs pa{};
         pa.seq2b = b.seq2b; pa.off = b.off; pa.len = b.len; pa.tile_start = ctx->sc_u64a.p;
         pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.mask = ctx->sc_mask.p;
+        pa.filter = ctx->d_filter; pa.filter_log2_words = ctx->filter_log2_words;
         unsigned blocks = (unsigned)((n_tiles + 7) / 8);
         unsigned max_blocks = (unsigned)ctx->sm_count * 4;
         if (blocks > max_blocks) blocks = max_blocks;
         {
             KernelTimer kt(ctx, FL_KERNEL_PROBE_PAINT);
-            switch (ctx->probe_mode) {
-                case 0: k_probe_paint<0><<<blocks, 256, 0, st>>>(pa); break;
-                case 2: k_probe_paint<2><<<blocks, 256, 0, st>>>(pa); break;
-                default: k_probe_paint<1><<<blocks, 256, 0, st>>>(pa); break;
+            // keep the pre-filter resident in the L2 set-aside while the probe kernel streams reads past it
+            const bool persist = ctx->use_filter && ctx->l2_persist_bytes > 0;
+            if (persist) {
+                cudaStreamAttrValue attr{};
+                attr.accessPolicyWindow.base_ptr = ctx->d_filter;
+                size_t bytes = ((size_t)1 << ctx->filter_log2_words) * sizeof(unsigned long long);
+                attr.accessPolicyWindow.num_bytes = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
+                attr.accessPolicyWindow.hitRatio = bytes <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)bytes;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+            }
+            if (ctx->use_filter) {
+                switch (ctx->probe_mode) {
+                    case 0: k_probe_paint<0, true><<<blocks, 256, 0, st>>>(pa); break;
+                    case 2: k_probe_paint<2, true><<<blocks, 256, 0, st>>>(pa); break;
+                    default: k_probe_paint<1, true><<<blocks, 256, 0, st>>>(pa); break;
+                }
+            } else {
+                switch (ctx->probe_mode) {
+                    case 0: k_probe_paint<0, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 2: k_probe_paint<2, false><<<blocks, 256, 0, st>>>(pa); break;
+                    default: k_probe_paint<1, false><<<blocks, 256, 0, st>>>(pa); break;
+                }
+            }
+            if (persist) {
+                cudaStreamAttrValue attr{};
+                attr.accessPolicyWindow.num_bytes = 0;
+                FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
             }
         }
         ctx->launches++;
