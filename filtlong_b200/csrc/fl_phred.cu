@@ -264,36 +264,35 @@ __global__ void __launch_bounds__(PH_THREADS, 3) k_phred_items(PhredArgs a) {
 // Mean chain of a LONG read, one warp per read, exact without walking it serially.
 //
 // The reference's sum (read.cpp:208-213) is s <- fl(s + q[c_j]) left to right. While s stays in one
-// binade [2^e, 2^(e+1)) it is a multiple of ulp_e = 2^(e-52), and for 0 <= q < 1
-//     fl(s + q) = s + ulp_e * round_half_even(q / ulp_e)                       (IEEE-754 RN)
-// so as long as no addend sits exactly on a rounding tie, a whole tile of additions is the INTEGER sum
-// of round(q/ulp_e) -- order free. u[c] = q[c] * 2^64 is an exact 64-bit integer for every Phred
-// value (q = 0 or 2^-11 <= q < 1), hence round(q/ulp_e) = (u + half) >> (e + 12) with the dropped
-// bits telling us about ties. A warp therefore adds 512 bases per step with one table gather and
-// a few integer ops per base plus one shuffle reduction; a step is redone by lane 0 with real
-// sequential double adds when (a) the tile would carry s into the next binade, (b) a tie or an
-// out-of-range quality byte occurs, or (c) e < 9 (start of the read). Those steps are rare (a
-// few dozen per read), every other step is exact by the identity above -- no speculation.
+// binade [2^e, 2^(e+1)) it is a multiple of ulp_e = 2^(e-52), and for 0 <= q < 1 (IEEE-754 RN)
+//     fl(s + q) = s + r(q),   r(q) = q rounded to a multiple of ulp_e,
+// unless q sits exactly half way between two multiples (tie: the result then depends on the parity
+// of s). r(q) itself is one add and one subtract of the constant C = 2^e (C + q stays in the binade
+// for e >= 9), and q - r(q) is exact, so a tie is |q - r(q)| == ulp_e / 2. All r(q) of a tile are
+// multiples of ulp_e below 1, their sum D < 2048 <= 2^(e+1) is exact in ANY order, and s + D is exact
+// as long as it stays below 2^(e+1). So a warp adds 2048 bases per step -- 64 per lane, one table
+// gather and four double ops per base, one shuffle reduction -- and only a step that (a) carries s
+// into the next binade, (b) contains a tie or a byte outside the Phred range, or (c) starts below
+// 2^11 is redone by lane 0 with the reference's own sequential adds. Those steps are a few dozen per
+// read; every other step is exact by the identity above (no speculation involved).
 // ---------------------------------------------------------------------------------------------
-#define PH_MEAN_SMEM (256 * 16 * 8 + 256 * 8)
+#define PH_MEAN_SMEM (256 * 16 * 8)
+#define PH_MEAN_TILE 2048
 
 __device__ __forceinline__ double serial_tile(const uint8_t *__restrict__ q, int lo, int hi, const double *__restrict__ qtab,
                                               double s) {
-    for (int j = lo; j < hi; ++j) s += qtab[q[j]];
+    for (int j = lo; j < hi; ++j) s += qtab[(unsigned)q[j] * 16];
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a, const unsigned long long *__restrict__ utab_g) {
+__global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *utab_all = reinterpret_cast<unsigned long long *>(smem_raw);     // [256][16]
-    double *qtab = reinterpret_cast<double *>(smem_raw + 256 * 16 * 8);                   // [256]
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) utab_all[i] = utab_g[i >> 4];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) qtab[i] = a.lut[i];
+    double *qtab_all = reinterpret_cast<double *>(smem_raw);                               // [256][16]
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) qtab_all[i] = a.lut[i >> 4];
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const unsigned long long *utab = utab_all + (lane & 15);
+    const double *qtab = qtab_all + (lane & 15);                 // lane-private bank pair
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const int ws = a.p.window_size;
     for (size_t r = warp; r < a.n; r += n_warps) {
         const size_t base = a.item_start[r];
         if (a.item_start[r + 1] - base <= 1) continue;           // short read: the fused item owns it
@@ -301,42 +300,46 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a, const unsi
         const uint8_t *q = a.qual + a.off[r];
         const uint4 *qv = reinterpret_cast<const uint4 *>(q);
         double s = 0.0;
-        const int head = L < 1024 ? L : 1024;                    // sum is still tiny here: plain sequential adds
-        if (lane == 0) s = serial_tile(q, 0, head, qtab, 0.0);
+        int j = L < 4096 ? L : 4096;                             // sum still small: plain sequential adds
+        if (lane == 0) s = serial_tile(q, 0, j, qtab, 0.0);
         s = __shfl_sync(0xffffffffu, s, 0);
-        for (int j = head; j < L; j += 512) {
-            const int hi = (j + 512 < L) ? j + 512 : L;
+        for (; j < L; j += PH_MEAN_TILE) {
+            const int hi = (j + PH_MEAN_TILE < L) ? j + PH_MEAN_TILE : L;
             int e = 0;
             (void)frexp(s, &e);
             e -= 1;                                              // s in [2^e, 2^(e+1))
-            const int sh = e + 12;
-            const bool lattice_ok = (s > 0.0) && e >= 9 && sh <= 62;
-            unsigned long long d = 0;
+            const bool lattice_ok = (s > 0.0) && e >= 11 && e <= 1000;
+            const double C = ldexp(1.0, e), half_ulp = ldexp(1.0, e - 53);
+            double d = 0.0;
             unsigned bad = lattice_ok ? 0u : 1u;
-            const int lo = j + 16 * (int)lane;
-            if (lattice_ok && lo < hi) {
-                const uint4 v = __ldg(qv + (lo >> 4));
-                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-                const unsigned long long mask = (1ull << sh) - 1ull, half = 1ull << (sh - 1);
+            if (lattice_ok) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (lo + k < hi) {
-                        const unsigned long long u = utab[byte_of(wv[k >> 2], k & 3) * 16];
-                        const unsigned long long low = u & mask;
-                        d += (u >> sh) + (low > half ? 1ull : 0ull);
-                        bad |= (low == half || u == ~0ull) ? 1u : 0u;
+                for (int c4 = 0; c4 < 4; ++c4) {                 // 4 coalesced 16-byte chunks per lane
+                    const int lo = j + 512 * c4 + 16 * (int)lane;
+                    if (lo < hi) {
+                        const uint4 v = __ldg(qv + (lo >> 4));
+                        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            const double x = qtab[byte_of(wv[k >> 2], k & 3) * 16];
+                            const double rq = (C + x) - C;       // x rounded to the grid of the binade
+                            const double res = fabs(x - rq);     // exact
+                            const bool in = lo + k < hi;
+                            bad |= (in && (!(x >= 0.0 && x < 1.0) || res == half_ulp)) ? 1u : 0u;
+                            d += in ? rq : 0.0;
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
-                d += __shfl_xor_sync(0xffffffffu, d, o);
+                d += __shfl_xor_sync(0xffffffffu, d, o);          // exact: multiples of ulp_e, total < 2^(e+1)
                 bad |= __shfl_xor_sync(0xffffffffu, bad, o);
             }
             bool done = false;
             if (!bad) {
-                const double s_new = s + ldexp((double)d, e - 52);   // exact: both multiples of ulp_e, d < 2^53
-                if (s_new < ldexp(1.0, e + 1)) { s = s_new; done = true; }
+                const double s_new = s + d;
+                if (s_new < C + C) { s = s_new; done = true; }
             }
             if (!done) {                                         // binade carry / tie / odd byte: the reference's own loop
                 if (lane == 0) s = serial_tile(q, j, hi, qtab, s);
@@ -344,7 +347,6 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a, const unsi
             }
         }
         if (lane == 0) a.it_a[base] = s;
-        (void)ws;
     }
 }
 
@@ -412,17 +414,6 @@ static int ensure_lut(fl_ctx *ctx) {
     fl_phred_luts(ctx->p.window_size, h, h + 256);
     if (!ctx->d_lut) FL_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(h)));
     FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-    // u[c] = q[c] * 2^64, exact for q == 0 or 2^-11 <= q < 1 (53 significant bits fit above 2^-64);
-    // anything else (bytes below '!' give negative / huge values) is marked ~0 = "walk serially"
-    unsigned long long u[256];
-    for (int c = 0; c < 256; ++c) {
-        const double q = h[c];
-        if (q == 0.0) u[c] = 0ull;
-        else if (q >= ldexp(1.0, -11) && q < 1.0) u[c] = (unsigned long long)ldexp(q, 64);
-        else u[c] = ~0ull;
-    }
-    if (!ctx->d_utab) FL_CUDA(ctx, cudaMalloc(&ctx->d_utab, sizeof(u)));
-    FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_utab, u, sizeof(u), cudaMemcpyHostToDevice, ctx->stream));
     FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->lut_window = ctx->p.window_size;
     return FL_OK;
@@ -489,7 +480,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     }
     ctx->launches++;
     if (n_items > n) {
-        k_phred_mean_long<<<ctx->sm_count * 8, 256, PH_MEAN_SMEM, st>>>(a, ctx->d_utab);
+        k_phred_mean_long<<<ctx->sm_count * 6, 256, PH_MEAN_SMEM, st>>>(a);
         ctx->launches++;
         k_phred_merge<<<fl_blocks(n, 256), 256, 0, st>>>(a);
         k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);
