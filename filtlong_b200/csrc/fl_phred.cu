@@ -300,21 +300,27 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
         const uint8_t *q = a.qual + a.off[r];
         const uint4 *qv = reinterpret_cast<const uint4 *>(q);
         double s = 0.0;
-        int j = L < 4096 ? L : 4096;                             // sum still small: plain sequential adds
-        if (lane == 0) s = serial_tile(q, 0, j, qtab, 0.0);
-        s = __shfl_sync(0xffffffffu, s, 0);
-        for (; j < L; j += PH_MEAN_TILE) {
-            const int hi = (j + PH_MEAN_TILE < L) ? j + PH_MEAN_TILE : L;
-            int e = 0;
-            (void)frexp(s, &e);
-            e -= 1;                                              // s in [2^e, 2^(e+1))
-            const bool lattice_ok = (s > 0.0) && e >= 11 && e <= 1000;
-            const double C = ldexp(1.0, e), half_ulp = ldexp(1.0, e - 53);
-            double d = 0.0;
-            unsigned bad = lattice_ok ? 0u : 1u;
+        int j = 0, small_left = 0;
+        while (j < L) {
+            int e = -2000;
+            if (s > 0.0) {
+                (void)frexp(s, &e);
+                e -= 1;                                          // s in [2^e, 2^(e+1))
+            }
+            // tile size: the exact-sum argument needs (bases in the tile) <= 2^(e+1); after a failed
+            // big tile the next 2048 bases are taken in 128-base pieces so that only the piece that
+            // really carries / ties is walked serially
+            const bool big = e >= 10 && e <= 1000 && small_left == 0;
+            const bool lattice_ok = big || (e >= 6 && e <= 1000);
+            const int T = big ? PH_MEAN_TILE : 128;
+            const int hi = (j + T < L) ? j + T : L;
+            bool done = false;
             if (lattice_ok) {
+                const double C = ldexp(1.0, e), half_ulp = ldexp(1.0, e - 53);
+                double d = 0.0;
+                unsigned bad = 0u;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {                 // 4 coalesced 16-byte chunks per lane
+                for (int c4 = 0; c4 < 4; ++c4) {                 // up to 4 coalesced 16-byte chunks per lane
                     const int lo = j + 512 * c4 + 16 * (int)lane;
                     if (lo < hi) {
                         const uint4 v = __ldg(qv + (lo >> 4));
@@ -330,21 +336,23 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
                         }
                     }
                 }
-            }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                d += __shfl_xor_sync(0xffffffffu, d, o);          // exact: multiples of ulp_e, total < 2^(e+1)
-                bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+                for (int o = 16; o; o >>= 1) {
+                    d += __shfl_xor_sync(0xffffffffu, d, o);      // exact: multiples of ulp_e, total < 2^(e+1)
+                    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+                }
+                if (!bad) {
+                    const double s_new = s + d;
+                    if (s_new < C + C) { s = s_new; done = true; }
+                }
             }
-            bool done = false;
-            if (!bad) {
-                const double s_new = s + d;
-                if (s_new < C + C) { s = s_new; done = true; }
-            }
-            if (!done) {                                         // binade carry / tie / odd byte: the reference's own loop
-                if (lane == 0) s = serial_tile(q, j, hi, qtab, s);
+            if (!done) {
+                if (big) { small_left = PH_MEAN_TILE / 128; continue; }   // retry this range in small pieces
+                if (lane == 0) s = serial_tile(q, j, hi, qtab, s);         // the reference's own loop
                 s = __shfl_sync(0xffffffffu, s, 0);
             }
+            if (small_left > 0) --small_left;
+            j = hi;
         }
         if (lane == 0) a.it_a[base] = s;
     }

@@ -50,9 +50,27 @@ struct ProbeArgs {
 // much HBM traffic a random probe costs (measured with ncu, profiles/): MODE 0 = ld.global.nc (L1
 // allocates and pulls whole 128-byte lines), 1 = ld.global.cg (L2 only, sector granular),
 // 2 = ld.global.nc.L1::no_allocate.
+// MODE 3 adds L2 eviction policies: the pre-filter is loaded evict_last, the bitmap probes and the
+// mask stores evict_first, so that streaming traffic does not push the filter out of L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 template <int MODE>
-__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t kmer) {
+__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t kmer, unsigned long long pol_first) {
     const uint32_t *p = bitmap + (kmer >> 5);
+    if (MODE == 3) {
+        uint32_t v;
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_first));
+        return v;
+    }
     if (MODE == 1) return __ldcg(p);
     if (MODE == 2) {
         uint32_t v;
@@ -65,6 +83,9 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
 template <int MODE, bool FILT>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
+    const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
+    const unsigned long long pol_last = MODE == 3 ? l2_policy_evict_last() : 0ull;
+    (void)pol_last;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     for (unsigned long long tile = warp; tile < a.n_tiles; tile += n_warps) {
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                 unsigned long long b = tile_base - 16 + lane;
                 if (b + (FL_K - 1) < (unsigned long long)L) {
                     uint32_t k = __funnelshift_l(wb, wa, 2 * lane);
-                    hit = (probe<MODE>(a.bitmap, k) >> (k & 31)) & 1u;
+                    hit = (probe<MODE>(a.bitmap, k, pol_first) >> (k & 31)) & 1u;
                 }
             }
             carry = __ballot_sync(0xffffffffu, hit) << 16;
@@ -112,7 +133,10 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         uint32_t word;
                         unsigned long long fb;
                         fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, word, fb);
-                        f[i] = (half * 16 + i < nvalid) ? __ldg(a.filter + word) : 0ull;
+                        if (half * 16 + i < nvalid) {
+                            if (MODE == 3) asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
+                            else f[i] = __ldg(a.filter + word);
+                        } else f[i] = 0ull;
                     }
                     go = 0;
 #pragma unroll
@@ -127,7 +151,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                 for (int i = 0; i < 16; ++i) {
                     const int p = half * 16 + i;
                     const uint32_t k = fl_kmer_at(w, p);
-                    words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(a.bitmap, k) : 0u;     // read.cpp:52
+                    words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(a.bitmap, k, pol_first) : 0u;     // read.cpp:52
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -144,7 +168,10 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             y |= y << 2;
             y |= y << 4;
             y |= y << 8;
-            if (lb < padded) maskw[lb >> 5] = (uint32_t)(y >> 32);
+            if (lb < padded) {
+                if (MODE == 3) asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(maskw + (lb >> 5)), "r"((uint32_t)(y >> 32)), "l"(pol_first));
+                else maskw[lb >> 5] = (uint32_t)(y >> 32);
+            }
             carry = __shfl_sync(0xffffffffu, h, 31);
         }
     }
@@ -484,12 +511,14 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                 switch (ctx->probe_mode) {
                     case 0: k_probe_paint<0, true><<<blocks, 256, 0, st>>>(pa); break;
                     case 2: k_probe_paint<2, true><<<blocks, 256, 0, st>>>(pa); break;
+                    case 3: k_probe_paint<3, true><<<blocks, 256, 0, st>>>(pa); break;
                     default: k_probe_paint<1, true><<<blocks, 256, 0, st>>>(pa); break;
                 }
             } else {
                 switch (ctx->probe_mode) {
                     case 0: k_probe_paint<0, false><<<blocks, 256, 0, st>>>(pa); break;
                     case 2: k_probe_paint<2, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 3: k_probe_paint<3, false><<<blocks, 256, 0, st>>>(pa); break;
                     default: k_probe_paint<1, false><<<blocks, 256, 0, st>>>(pa); break;
                 }
             }
