@@ -104,7 +104,8 @@ struct fl_ctx {
     uint64_t n_kmers = 0;
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
-    unsigned filter_log2_words = 23;     // 2^23 x 8 B = 64 MiB
+    unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
+    int filter_kind = 0;                 // 0: word from a hash of the k-mer, 1: from its minimizer (FL_FILTER_KIND)
     bool use_filter = false;
     int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside granted to this context

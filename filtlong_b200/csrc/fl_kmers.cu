@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_popcount(const uint32_t *__restrict__ b
 
 // pre-filter build: every member of the bitmap sets its two filter bits
 __global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict__ bm, unsigned long long *__restrict__ filter,
-                                                      unsigned log2_words) {
+                                                      unsigned log2_words, int kind) {
     const size_t n_words = (size_t)1 << 27;
     for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
         uint32_t bits = bm[w];
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict
             bits &= bits - 1;
             uint32_t word;
             unsigned long long fb;
-            fl_filter_slot((uint32_t)(w << 5) | (uint32_t)b, log2_words, word, fb);
+            fl_filter_slot((uint32_t)(w << 5) | (uint32_t)b, log2_words, kind, word, fb);
             if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
         }
     }
@@ -299,7 +299,7 @@ int fl_kmers_recount(fl_ctx *ctx) {
     if (ctx->use_filter) {
         if (!ctx->d_filter) FL_CUDA(ctx, cudaMalloc(&ctx->d_filter, filter_words * sizeof(unsigned long long)));
         FL_CUDA(ctx, cudaMemsetAsync(ctx->d_filter, 0, filter_words * sizeof(unsigned long long), ctx->stream));
-        k_filter_build<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->d_bitmap, ctx->d_filter, ctx->filter_log2_words);
+        k_filter_build<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->d_bitmap, ctx->d_filter, ctx->filter_log2_words, ctx->filter_kind);
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
     }

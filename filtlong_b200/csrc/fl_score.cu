@@ -43,6 +43,7 @@ struct ProbeArgs {
     const uint32_t *bitmap;
     const unsigned long long *filter;        // L2-resident pre-filter (fl_kmers.cu), used when FILT
     unsigned filter_log2_words;
+    int filter_kind;
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
 };
 
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     for (int i = 0; i < 16; ++i) {
                         uint32_t word;
                         unsigned long long fb;
-                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, word, fb);
+                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         if (half * 16 + i < nvalid) {
                             if (MODE == 3) asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
                             else f[i] = __ldg(a.filter + word);
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     for (int i = 0; i < 16; ++i) {
                         uint32_t word;
                         unsigned long long fb;
-                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, word, fb);
+                        fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
                     }
                 }
@@ -489,7 +490,7 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         ProbeArgs pa{};
         pa.seq2b = b.seq2b; pa.off = b.off; pa.len = b.len; pa.tile_start = ctx->sc_u64a.p;
         pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.mask = ctx->sc_mask.p;
-        pa.filter = ctx->d_filter; pa.filter_log2_words = ctx->filter_log2_words;
+        pa.filter = ctx->d_filter; pa.filter_log2_words = ctx->filter_log2_words; pa.filter_kind = ctx->filter_kind;
         unsigned blocks = (unsigned)((n_tiles + 7) / 8);
         unsigned max_blocks = (unsigned)ctx->sm_count * 4;
         if (blocks > max_blocks) blocks = max_blocks;
