@@ -70,6 +70,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     }
     if (const char *f = getenv("FL_FILTER_LOG2_WORDS")) c->filter_log2_words = (unsigned)atoi(f);
     if (const char *f = getenv("FL_FILTER_KIND")) c->filter_kind = atoi(f);
+    if (const char *f = getenv("FL_FILTER_MIN_BITS")) c->filter_min_bits_per_key = atoi(f);
     if (const char *g = getenv("FL_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     *out = c;
     return FL_OK;

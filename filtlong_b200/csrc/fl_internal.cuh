@@ -108,6 +108,7 @@ struct fl_ctx {
     int filter_kind = 0;                 // 0: word from a hash of the k-mer, 1: from its minimizer (FL_FILTER_KIND)
     bool use_filter = false;
     int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
+    int filter_min_bits_per_key = 8;     // the filter is used while it has at least this many bits per member
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside granted to this context
     bool kmers_count_stale = false;
     // multiple-copy build state (kmers.cpp:142-166 in closed form, see fl_kmers.cu)

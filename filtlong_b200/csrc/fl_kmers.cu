@@ -295,7 +295,7 @@ int fl_kmers_recount(fl_ctx *ctx) {
     // rate of the two-bit test below ~5 %). Larger sets (e.g. a 3 Gbp assembly fills 75 % of the key
     // space) are probed directly.
     const size_t filter_words = (size_t)1 << ctx->filter_log2_words;
-    ctx->use_filter = ctx->filter_enabled && ctx->n_kmers > 0 && ctx->n_kmers * 8 <= filter_words * 64;
+    ctx->use_filter = ctx->filter_enabled && ctx->n_kmers > 0 && ctx->n_kmers * (uint64_t)ctx->filter_min_bits_per_key <= filter_words * 64;
     if (ctx->use_filter) {
         if (!ctx->d_filter) FL_CUDA(ctx, cudaMalloc(&ctx->d_filter, filter_words * sizeof(unsigned long long)));
         FL_CUDA(ctx, cudaMemsetAsync(ctx->d_filter, 0, filter_words * sizeof(unsigned long long), ctx->stream));
