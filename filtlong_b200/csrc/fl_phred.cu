@@ -28,7 +28,7 @@
 
 namespace {
 
-#define PH_THREADS 256
+#define PH_THREADS 1024
 #define PH_SMEM (256 * 8 * 16 + 256 * 16 * 8)   // {q,a} x 8 copies + a x 16 copies = 64 KiB
 #define PH_SEG 16384
 #define PH_LONG (PH_SEG + PH_SEG / 2)
@@ -242,7 +242,7 @@ __device__ __forceinline__ Tab make_tables(const double *lut, unsigned char *sme
     return t;
 }
 
-__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_items(PhredArgs a) {
+__global__ void __launch_bounds__(PH_THREADS, 1) k_phred_items(PhredArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tab t = make_tables(a.lut, smem_raw);
     const size_t T = (size_t)gridDim.x * blockDim.x;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) k_phred_merge(PhredArgs a) {
     else a.fallback[1 + atomicAdd(a.fallback, 1u)] = r;
 }
 
-__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_fallback(PhredArgs a) {
+__global__ void __launch_bounds__(PH_THREADS, 1) k_phred_fallback(PhredArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = a.fallback[0];
     if (n == 0) return;
@@ -480,7 +480,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         attr_set = true;
     }
     unsigned blocks = fl_blocks(n_items, PH_THREADS);
-    const unsigned max_blocks = (unsigned)ctx->sm_count * 3;
+    const unsigned max_blocks = (unsigned)ctx->sm_count * 1;
     if (blocks > max_blocks) blocks = max_blocks;
     {
         KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
