@@ -102,7 +102,7 @@ __device__ __forceinline__ unsigned fl_length_bucket(int len) {
 // the L2 sees ~3x fewer requests; the two bit positions still come from the whole k-mer.
 __device__ __forceinline__ void fl_filter_slot(uint32_t kmer, unsigned log2_words, int kind, uint32_t &word, unsigned long long &bits) {
     uint32_t h1 = kmer * 0x9E3779B1u;
-    if (kind == 1) {
+    if (kind & 1) {
         h1 = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         if (half * 16 + i < nvalid) {
                             if (MODE == 3) asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
+                            else if (a.filter_kind & 2) f[i] = __ldcg(a.filter + word);   // L2 only (no L1 line fill)
                             else f[i] = __ldg(a.filter + word);
                         } else f[i] = 0ull;
                     }
