@@ -46,6 +46,8 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaMalloc(&c->d_scalars, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMemset(c->d_scalars, 0, 64 * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMallocHost(&c->h_scalars, 64 * sizeof(unsigned long long))) != cudaSuccess) {
@@ -92,6 +94,9 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
     fl_norm_select_free(c);
+    for (int i = 0; i < 2; ++i) if (c->stg[i].consumed) cudaEventDestroy(c->stg[i].consumed);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -201,35 +206,45 @@ static int check_batch(fl_ctx *c, const fl_batch *b) {
     return FL_OK;
 }
 
-static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool want_seq, bool want_qual, bool want_nmask) {
-    cudaStream_t s = c->stream;
+static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool want_seq, bool want_qual, bool want_nmask,
+                            int slot, cudaStream_t s) {
+    fl_ctx::Staging &S = c->stg[slot];
     const size_t n = h->n;
-    FL_CUDA(c, c->st_off.reserve(n, 0, s));
-    FL_CUDA(c, c->st_len.reserve(n, 0, s));
-    FL_CUDA(c, cudaMemcpyAsync(c->st_off.p, h->off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    FL_CUDA(c, cudaMemcpyAsync(c->st_len.p, h->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    FL_CUDA(c, S.off.reserve(n, 0, s));
+    FL_CUDA(c, S.len.reserve(n, 0, s));
+    FL_CUDA(c, cudaMemcpyAsync(S.off.p, h->off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    FL_CUDA(c, cudaMemcpyAsync(S.len.p, h->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     v->n = h->n;
     v->padded_bases = h->padded_bases;
-    v->off = c->st_off.p;
-    v->len = c->st_len.p;
+    v->off = S.off.p;
+    v->len = S.len.p;
     v->seq2b = nullptr; v->qual = nullptr; v->nmask = nullptr;
     if (want_seq && h->seq2b) {
         size_t words = (size_t)(h->padded_bases >> 4);
-        FL_CUDA(c, c->st_seq.reserve(words + 4, 0, s));
-        FL_CUDA(c, cudaMemcpyAsync(c->st_seq.p, h->seq2b, words * 4, cudaMemcpyHostToDevice, s));
-        v->seq2b = c->st_seq.p;
+        FL_CUDA(c, S.seq.reserve(words + 4, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(S.seq.p, h->seq2b, words * 4, cudaMemcpyHostToDevice, s));
+        v->seq2b = S.seq.p;
     }
     if (want_qual && h->qual) {
-        FL_CUDA(c, c->st_qual.reserve((size_t)h->padded_bases + 64, 0, s));
-        FL_CUDA(c, cudaMemcpyAsync(c->st_qual.p, h->qual, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
-        v->qual = c->st_qual.p;
+        FL_CUDA(c, S.qual.reserve((size_t)h->padded_bases + 64, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(S.qual.p, h->qual, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
+        v->qual = S.qual.p;
     }
     if (want_nmask && h->nmask) {
         size_t words = (size_t)(h->padded_bases >> 5);
-        FL_CUDA(c, c->st_nmask.reserve(words + 4, 0, s));
-        FL_CUDA(c, cudaMemcpyAsync(c->st_nmask.p, h->nmask, words * 4, cudaMemcpyHostToDevice, s));
-        v->nmask = c->st_nmask.p;
+        FL_CUDA(c, S.nmask.reserve(words + 4, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(S.nmask.p, h->nmask, words * 4, cudaMemcpyHostToDevice, s));
+        v->nmask = S.nmask.p;
     }
+    return FL_OK;
+}
+
+// waits until no kernel still reads staging slot `slot`
+static int staging_acquire(fl_ctx *c, int slot) {
+    fl_ctx::Staging &S = c->stg[slot];
+    if (!S.consumed) FL_CUDA(c, cudaEventCreateWithFlags(&S.consumed, cudaEventDisableTiming));
+    if (S.in_use) FL_CUDA(c, cudaEventSynchronize(S.consumed));
+    S.in_use = false;
     return FL_OK;
 }
 
@@ -245,7 +260,8 @@ extern "C" int fl_kmers_add_batch(fl_ctx *c, const fl_batch *h, int multi) {
     FL_TRY(check_batch(c, h));
     if (h->n == 0) return FL_OK;
     BatchView v{};
-    FL_TRY(stage_host_batch(c, h, &v, true, false, true));
+    FL_TRY(staging_acquire(c, 0));
+    FL_TRY(stage_host_batch(c, h, &v, true, false, true, 0, c->stream));
     FL_TRY(fl_kmers_add_view(c, v, multi));
     FL_CUDA(c, cudaStreamSynchronize(c->stream));   // staging buffers are reused by the next call
     return FL_OK;
@@ -274,10 +290,19 @@ extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
     if (c->kmers_count_stale || c->multi_pending) FL_TRY(fl_kmers_recount(c));
     const bool kmer_mode = c->n_kmers > 0;
     BatchView v{};
-    FL_TRY(stage_host_batch(c, h, &v, kmer_mode, !kmer_mode, false));
+    // double-buffered staging: this batch's host->device copies run on the copy stream while the
+    // kernels of the previous batch are still busy on the compute stream
+    const int slot = c->stg_next;
+    c->stg_next ^= 1;
+    FL_TRY(staging_acquire(c, slot));
+    FL_TRY(stage_host_batch(c, h, &v, kmer_mode, !kmer_mode, false, slot, c->copy_stream));
+    FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+    FL_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
     FL_TRY(fl_score_view(c, v));
+    FL_CUDA(c, cudaEventRecord(c->stg[slot].consumed, c->stream));
+    c->stg[slot].in_use = true;
     for (uint32_t i = 0; i < h->n; ++i) c->total_bases += h->len[i];     // main.cpp:89
-    FL_CUDA(c, cudaStreamSynchronize(c->stream));   // staging buffers are reused by the next call
+    FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the caller may reuse its host buffers now
     return FL_OK;
 }
 

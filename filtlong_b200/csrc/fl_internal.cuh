@@ -125,10 +125,18 @@ struct fl_ctx {
     int lut_window = -1;
 
     // ---- staging for host batches ----
-    DevVec<uint64_t> st_off;
-    DevVec<int32_t> st_len;
-    DevVec<uint32_t> st_seq, st_nmask;
-    DevVec<uint8_t> st_qual;
+    // two slots: the host->device copy of batch i+1 (copy_stream) overlaps the kernels of batch i
+    struct Staging {
+        DevVec<uint64_t> off;
+        DevVec<int32_t> len;
+        DevVec<uint32_t> seq, nmask;
+        DevVec<uint8_t> qual;
+        cudaEvent_t consumed = nullptr;   // recorded on the compute stream after the last kernel that reads this slot
+        bool in_use = false;
+    } stg[2];
+    int stg_next = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied = nullptr;
 
     // ---- per-batch scratch ----
     DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer

@@ -276,3 +276,25 @@ def test_bloom_false_positive_kat_912k_reads():
     ctx.kmers_release_build_state()
     ctx.close()
     assert n == 25225
+
+
+def test_kmer_results_do_not_depend_on_batching():
+    """fl_reads_push double-buffers its staging (copy of batch i+1 overlaps the kernels of batch
+    i): pushing the same reads as 1, 3 or 7 batches must give identical rows."""
+    rng, genome, genome_n, reads = make_kmer_case(55, n_reads=90)
+    opts = dict(keep_percent=80.0, trim=True, split=100)
+    outs = []
+    for n_batches in (1, 3, 7):
+        ctx = api.Context(api.make_params(**opts))
+        ctx.kmers_add([genome_n], False)
+        step = (len(reads) + n_batches - 1) // n_batches
+        total = 0
+        for i in range(0, len(reads), step):
+            hb = api.HostBatch([r[0] for r in reads[i:i + step]], [r[1] for r in reads[i:i + step]])
+            ctx.push(hb)
+            total += hb.total_bases
+        summ = ctx.finalize(total)
+        rw = ctx.row_results()
+        outs.append((summ.keeping, summ.target, {k: v.tobytes() for k, v in rw.items()}))
+        ctx.close()
+    assert outs[0] == outs[1] == outs[2]
