@@ -61,7 +61,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
     {
         const char *pe = getenv("FL_L2_PERSIST");
-        if (!pe || atoi(pe) != 0) {
+        if (pe && atoi(pe) != 0) {   // off by default: measured slower (the set-aside shrinks the normal L2)
             size_t want = (size_t)prop.persistingL2CacheMaxSize;
             if (want > ((size_t)96 << 20)) want = (size_t)96 << 20;
             if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {

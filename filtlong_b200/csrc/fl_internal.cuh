@@ -105,7 +105,7 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    int filter_kind = 0;                 // 0: word from a hash of the k-mer, 1: from its minimizer (FL_FILTER_KIND)
+    int filter_kind = 2;                 // bit 0: word from the k-mer minimizer instead of a plain hash; bit 1: load the filter with ld.global.cg (FL_FILTER_KIND)
     bool use_filter = false;
     int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
     int filter_min_bits_per_key = 8;     // the filter is used while it has at least this many bits per member
@@ -121,6 +121,7 @@ struct fl_ctx {
 
     // ---- Phred LUTs ----
     double *d_lut = nullptr;   // [0..256) q, [256..512) a = q / window_size
+    unsigned long long tie_binades = 0;     // bit e: some Phred table value ties when added to a sum in [2^e, 2^(e+1))
     unsigned long long *d_utab = nullptr;   // [256] q * 2^64 as exact integers (~0 = not representable), fl_phred.cu
     int lut_window = -1;
 

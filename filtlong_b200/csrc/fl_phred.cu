@@ -28,7 +28,7 @@
 
 namespace {
 
-#define PH_THREADS 1024
+#define PH_THREADS 256
 #define PH_SMEM (256 * 8 * 16 + 256 * 16 * 8)   // {q,a} x 8 copies + a x 16 copies = 64 KiB
 #define PH_SEG 16384
 #define PH_LONG (PH_SEG + PH_SEG / 2)
@@ -242,7 +242,7 @@ __device__ __forceinline__ Tab make_tables(const double *lut, unsigned char *sme
     return t;
 }
 
-__global__ void __launch_bounds__(PH_THREADS, 1) k_phred_items(PhredArgs a) {
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_items(PhredArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tab t = make_tables(a.lut, smem_raw);
     const size_t T = (size_t)gridDim.x * blockDim.x;
@@ -281,14 +281,19 @@ __global__ void __launch_bounds__(PH_THREADS, 1) k_phred_items(PhredArgs a) {
 
 __device__ __forceinline__ double serial_tile(const uint8_t *__restrict__ q, int lo, int hi, const double *__restrict__ qtab,
                                               double s) {
-    for (int j = lo; j < hi; ++j) s += qtab[(unsigned)q[j] * 16];
+    for (int j = lo; j < hi; ++j) s += __ldg(qtab + (unsigned)q[j]);     // true table (global), rare path
     return s;
 }
 
-__global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
+__global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a, unsigned long long tie_binades) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *qtab_all = reinterpret_cast<double *>(smem_raw);                               // [256][16]
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) qtab_all[i] = a.lut[i >> 4];
+    // grid-path table: a quality outside [0, 1) becomes NaN, which poisons the tile sum and sends the
+    // tile to the serial path without any per-base range test
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const double v = a.lut[i >> 4];
+        qtab_all[i] = (v >= 0.0 && v < 1.0) ? v : __longlong_as_double(0x7FF8000000000000ll);
+    }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
     const double *qtab = qtab_all + (lane & 15);                 // lane-private bank pair
@@ -317,6 +322,10 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
             bool done = false;
             if (lattice_ok) {
                 const double C = ldexp(1.0, e), half_ulp = ldexp(1.0, e - 53);
+                // a rounding tie needs a table value whose dropped bits are exactly 100..0 in this
+                // binade; the host lists the binades where ANY Phred value does (none above 2^9 for
+                // the default table), everywhere else the per-base tie test is skipped
+                const bool check_ties = e < 64 && ((tie_binades >> e) & 1ull);
                 double d = 0.0;
                 unsigned bad = 0u;
 #pragma unroll
@@ -325,14 +334,21 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
                     if (lo < hi) {
                         const uint4 v = __ldg(qv + (lo >> 4));
                         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                        if (lo + 16 <= hi && !check_ties) {
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) {
-                            const double x = qtab[byte_of(wv[k >> 2], k & 3) * 16];
-                            const double rq = (C + x) - C;       // x rounded to the grid of the binade
-                            const double res = fabs(x - rq);     // exact
-                            const bool in = lo + k < hi;
-                            bad |= (in && (!(x >= 0.0 && x < 1.0) || res == half_ulp)) ? 1u : 0u;
-                            d += in ? rq : 0.0;
+                            for (int k = 0; k < 16; ++k) {
+                                const double x = qtab[byte_of(wv[k >> 2], k & 3) * 16];
+                                d += (C + x) - C;                // x rounded to the grid of the binade
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                const double x = qtab[byte_of(wv[k >> 2], k & 3) * 16];
+                                const double rq = (C + x) - C;
+                                const bool in = lo + k < hi;
+                                bad |= (in && fabs(x - rq) == half_ulp) ? 1u : 0u;   // x - rq is exact
+                                d += in ? rq : 0.0;
+                            }
                         }
                     }
                 }
@@ -348,7 +364,7 @@ __global__ void __launch_bounds__(256) k_phred_mean_long(PhredArgs a) {
             }
             if (!done) {
                 if (big) { small_left = PH_MEAN_TILE / 128; continue; }   // retry this range in small pieces
-                if (lane == 0) s = serial_tile(q, j, hi, qtab, s);         // the reference's own loop
+                if (lane == 0) s = serial_tile(q, j, hi, a.lut, s);        // the reference's own loop
                 s = __shfl_sync(0xffffffffu, s, 0);
             }
             if (small_left > 0) --small_left;
@@ -379,7 +395,7 @@ __global__ void __launch_bounds__(256) k_phred_merge(PhredArgs a) {
     else a.fallback[1 + atomicAdd(a.fallback, 1u)] = r;
 }
 
-__global__ void __launch_bounds__(PH_THREADS, 1) k_phred_fallback(PhredArgs a) {
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_fallback(PhredArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t n = a.fallback[0];
     if (n == 0) return;
@@ -422,6 +438,16 @@ static int ensure_lut(fl_ctx *ctx) {
     fl_phred_luts(ctx->p.window_size, h, h + 256);
     if (!ctx->d_lut) FL_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(h)));
     FL_CUDA(ctx, cudaMemcpyAsync(ctx->d_lut, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    // binades [2^e, 2^(e+1)) of the running sum in which some table value in [0,1) would sit exactly
+    // on a rounding tie (its bits below 2^(e-52) are 100..0): only there k_phred_mean_long tests ties
+    ctx->tie_binades = 0;
+    for (int e = 0; e < 64; ++e)
+        for (int c = 0; c < 256; ++c) {
+            const double q = h[c];
+            if (!(q > 0.0 && q < 1.0)) continue;
+            const double scaled = ldexp(q, 52 - e);          // exact
+            if (scaled - floor(scaled) == 0.5) ctx->tie_binades |= 1ull << e;
+        }
     FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->lut_window = ctx->p.window_size;
     return FL_OK;
@@ -480,7 +506,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         attr_set = true;
     }
     unsigned blocks = fl_blocks(n_items, PH_THREADS);
-    const unsigned max_blocks = (unsigned)ctx->sm_count * 1;
+    const unsigned max_blocks = (unsigned)ctx->sm_count * 3;
     if (blocks > max_blocks) blocks = max_blocks;
     {
         KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
@@ -488,7 +514,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     }
     ctx->launches++;
     if (n_items > n) {
-        k_phred_mean_long<<<ctx->sm_count * 6, 256, PH_MEAN_SMEM, st>>>(a);
+        k_phred_mean_long<<<ctx->sm_count * 6, 256, PH_MEAN_SMEM, st>>>(a, ctx->tie_binades);
         ctx->launches++;
         k_phred_merge<<<fl_blocks(n, 256), 256, 0, st>>>(a);
         k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);
