@@ -97,7 +97,7 @@ struct fl_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
-    int probe_mode = 1;        // load flavour of the bitmap probe (fl_score.cu); FL_PROBE_MODE overrides for experiments
+    int probe_mode = 2;        // load flavour of the bitmap probe (fl_score.cu; 2 = ld.global.nc.L1::no_allocate, measured best); FL_PROBE_MODE overrides
 
     // ---- Kmers ----
     uint32_t *d_bitmap = nullptr;        // 2^32 bits, direct-address membership
