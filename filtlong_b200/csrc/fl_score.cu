@@ -366,6 +366,7 @@ __device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, i
     };
     for (; (pin & 31) && pin < E; ++pin, ++pout)
         step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
+    const bool long_row = len >= 32768;
     if (pin + 32 <= E) {
         const unsigned sh = (unsigned)(pout & 31);       // constant from here on
         int ow_idx = pout >> 5;
@@ -374,8 +375,38 @@ __device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, i
             const uint32_t inw = m[pin >> 5];
             const uint32_t ohi = m[ow_idx + 1];          // within the parent's padded mask: pout + 32 + 31 < pin + 32 <= E
             const uint32_t outw = __funnelshift_r(olo, ohi, sh);
+            if (!long_row) {
 #pragma unroll
-            for (int t = 0; t < 32; ++t) step((inw >> t) & 1u, (outw >> t) & 1u);
+                for (int t = 0; t < 32; ++t) step((inw >> t) & 1u, (outw >> t) & 1u);
+            } else {
+                // Long rows are the kernel's serial tail, so they walk the word by RUNS: a step with
+                // both bits 0 adds and subtracts 0.0 (no change); a step with both bits 1 maps w to
+                // g(w) = fl(fl(w - r) + r), and once g(w) == w every further (1,1) step is a no-op
+                // too, so g is applied until its fixed point (almost always at once); only steps
+                // whose bits differ really move w. Same values as the bit loop, step for step. (For
+                // short rows the data-dependent trip count diverges across the warp and loses.)
+                const uint32_t diff = inw ^ outw, both = inw & outw;
+                int t = 0;
+                while (t < 32) {
+                    const uint32_t rem = diff >> t;
+                    const int nd = rem ? t + (__ffs(rem) - 1) : 32;      // next step whose bits differ
+                    if (nd > t) {
+                        const uint32_t stretch = (nd - t == 32) ? 0xFFFFFFFFu : (((1u << (nd - t)) - 1u) << t);
+                        int c11 = __popc(both & stretch);
+                        while (c11-- > 0) {
+                            const double w2 = (w - rq) + rq;                 // read.cpp:229-230, both qualities 1
+                            if (w2 == w) break;
+                            w = w2;
+                            if (w < best) best = w;
+                        }
+                    }
+                    if (nd >= 32) break;
+                    if ((inw >> nd) & 1u) { w -= 0.0; w += rq; }             // base enters a k-mer match
+                    else { w -= rq; w += 0.0; }                              // base leaves one
+                    if (w < best) best = w;
+                    t = nd + 1;
+                }
+            }
             olo = ohi;
             ++ow_idx;
         }
