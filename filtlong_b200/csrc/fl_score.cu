@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(256) k_kmer_rows(RowArgs a) {
 // The k-mer-mode quality of a base is exactly 0.0 or 1.0 (read.cpp:42,55), so the mean's sequential
 // sum is an exact integer, and the window recurrence adds / subtracts r = 1.0 / ws or 0.0 in the
 // reference's order (read.cpp:226-232) -- bit-identical, including its rounding drift.
+template <bool RUNS>
 __device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, int S, int E, int ws, double *mean_out,
                                                double *window_out) {
     const int len = E - S;
@@ -366,7 +367,6 @@ __device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, i
     };
     for (; (pin & 31) && pin < E; ++pin, ++pout)
         step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
-    const bool long_row = len >= 32768;
     if (pin + 32 <= E) {
         const unsigned sh = (unsigned)(pout & 31);       // constant from here on
         int ow_idx = pout >> 5;
@@ -375,16 +375,17 @@ __device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, i
             const uint32_t inw = m[pin >> 5];
             const uint32_t ohi = m[ow_idx + 1];          // within the parent's padded mask: pout + 32 + 31 < pin + 32 <= E
             const uint32_t outw = __funnelshift_r(olo, ohi, sh);
-            if (!long_row) {
+            if (!RUNS) {
 #pragma unroll
                 for (int t = 0; t < 32; ++t) step((inw >> t) & 1u, (outw >> t) & 1u);
             } else {
-                // Long rows are the kernel's serial tail, so they walk the word by RUNS: a step with
+                // Long rows are the serial tail; they run in k_kmer_stats_long with ONE active lane per warp
+                // (no divergence) and walk the word by RUNS: a step with
                 // both bits 0 adds and subtracts 0.0 (no change); a step with both bits 1 maps w to
                 // g(w) = fl(fl(w - r) + r), and once g(w) == w every further (1,1) step is a no-op
                 // too, so g is applied until its fixed point (almost always at once); only steps
-                // whose bits differ really move w. Same values as the bit loop, step for step. (For
-                // short rows the data-dependent trip count diverges across the warp and loses.)
+                // whose bits differ really move w. Same values as the bit loop, step for step. (With 32
+                // rows per warp the data-dependent trip counts diverge and this loses -- measured.)
                 const uint32_t diff = inw ^ outw, both = inw & outw;
                 int t = 0;
                 while (t < 32) {
@@ -436,25 +437,39 @@ struct StatArgs {
     const uint8_t *r_passed;
 };
 
+#define FL_LONG_ROW 131072      // rows at least this long go to k_kmer_stats_long (a length-bucket boundary)
+
+__device__ __forceinline__ bool stat_row(const StatArgs &a, uint32_t row, bool long_pass) {
+    const uint32_t r = (uint32_t)(a.w_parent[row] - a.read_base);
+    const int S = a.w_start[row], E = a.w_end[row];
+    const bool is_long = (E - S) >= FL_LONG_ROW;
+    if (is_long != long_pass) return is_long;
+    if (a.r_nchild && a.r_nchild[r] == 0) {
+        a.w_mean[row] = a.r_mean[r];
+        a.w_window[row] = a.r_window[r];
+        a.w_passed[row] = a.r_passed[r];
+        return is_long;
+    }
+    const uint32_t *m = a.mask + (a.off[r] >> 5);
+    double mean, window;
+    if (long_pass) kmer_row_stats<true>(m, S, E, a.p.window_size, &mean, &window);
+    else kmer_row_stats<false>(m, S, E, a.p.window_size, &mean, &window);
+    a.w_mean[row] = mean;
+    a.w_window[row] = window;
+    a.w_passed[row] = fl_hard_cutoffs(a.p, E - S, mean, window);
+    return is_long;
+}
+
 __global__ void __launch_bounds__(256) k_kmer_stats(StatArgs a) {
     const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n_rows; it += T) {
-        const uint32_t row = a.order[it];
-        const uint32_t r = (uint32_t)(a.w_parent[row] - a.read_base);
-        if (a.r_nchild && a.r_nchild[r] == 0) {
-            a.w_mean[row] = a.r_mean[r];
-            a.w_window[row] = a.r_window[r];
-            a.w_passed[row] = a.r_passed[r];
-            continue;
-        }
-        const int S = a.w_start[row], E = a.w_end[row];
-        const uint32_t *m = a.mask + (a.off[r] >> 5);
-        double mean, window;
-        kmer_row_stats(m, S, E, a.p.window_size, &mean, &window);
-        a.w_mean[row] = mean;
-        a.w_window[row] = window;
-        a.w_passed[row] = fl_hard_cutoffs(a.p, E - S, mean, window);
-    }
+    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n_rows; it += T) stat_row(a, a.order[it], false);
+}
+
+// one warp per long row, lane 0 only: rows are ordered longest first, so the long ones are a prefix
+__global__ void __launch_bounds__(32) k_kmer_stats_long(StatArgs a) {
+    if (threadIdx.x != 0) return;
+    for (size_t it = blockIdx.x; it < a.n_rows; it += gridDim.x)
+        if (!stat_row(a, a.order[it], true)) break;
 }
 
 __global__ void k_iota(uint32_t *p, uint32_t n, uint32_t base) {
@@ -598,9 +613,10 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
         {
             KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
+            k_kmer_stats_long<<<(unsigned)ctx->sm_count * 32, 32, 0, st>>>(sa);
             k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
         }
-        ctx->launches++;
+        ctx->launches += 2;
     }
     // ---- rows ----
     const bool may_have_children = ctx->p.trim || ctx->p.split_set;
@@ -643,9 +659,10 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
         {
             KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
+            k_kmer_stats_long<<<(unsigned)ctx->sm_count * 32, 32, 0, st>>>(sa);
             k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
         }
-        ctx->launches++;
+        ctx->launches += 2;
     }
     FL_CUDA(ctx, cudaGetLastError());
     ctx->n_reads += n;
