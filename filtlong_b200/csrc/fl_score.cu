@@ -437,7 +437,10 @@ struct StatArgs {
     const uint8_t *r_passed;
 };
 
-#define FL_LONG_ROW 131072      // rows at least this long go to k_kmer_stats_long (a length-bucket boundary)
+// Measured (profiles/r01 launch lists): walking long rows by runs with one lane per warp
+// (k_kmer_stats_long) is 3x SLOWER on noisy hit masks than the unrolled bit loop, so every row takes
+// the bit loop; the threshold is kept only so the experiment can be repeated.
+#define FL_LONG_ROW 0x7FFFFFFF
 
 __device__ __forceinline__ bool stat_row(const StatArgs &a, uint32_t row, bool long_pass) {
     const uint32_t r = (uint32_t)(a.w_parent[row] - a.read_base);
@@ -613,10 +616,9 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
         {
             KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
-            k_kmer_stats_long<<<(unsigned)ctx->sm_count * 32, 32, 0, st>>>(sa);
             k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
         }
-        ctx->launches += 2;
+        ctx->launches++;
     }
     // ---- rows ----
     const bool may_have_children = ctx->p.trim || ctx->p.split_set;
@@ -659,10 +661,9 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         if (blocks > stat_blocks_max) blocks = stat_blocks_max;
         {
             KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
-            k_kmer_stats_long<<<(unsigned)ctx->sm_count * 32, 32, 0, st>>>(sa);
             k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
         }
-        ctx->launches += 2;
+        ctx->launches++;
     }
     FL_CUDA(ctx, cudaGetLastError());
     ctx->n_reads += n;
