@@ -298,3 +298,86 @@ def test_kmer_results_do_not_depend_on_batching():
         outs.append((summ.keeping, summ.target, {k: v.tobytes() for k, v in rw.items()}))
         ctx.close()
     assert outs[0] == outs[1] == outs[2]
+
+
+def _two_shard_finalize(ctxs, total_bases):
+    """Runs the split-phase normalise/select protocol of filtlong_b200/sharding.py over two contexts
+    on ONE GPU, with the all-reduces done by hand on the device buffers (what NCCL does between
+    ranks). Returns the per-context summaries."""
+    import torch
+    from filtlong_b200 import sharding
+    world = len(ctxs)
+    bks = [sharding.CabiBackend(c) for c in ctxs]
+    bufs = [sharding.Buffers(torch, "cuda", world) for _ in ctxs]
+
+    def allreduce(name, op="sum"):
+        ts = [getattr(b, name) for b in bufs]
+        for c in ctxs:
+            c.sync()
+        torch.cuda.synchronize()
+        st = torch.stack(ts)
+        red = st.sum(0) if op == "sum" else (st.min(0).values if op == "min" else st.max(0).values)
+        for t in ts:
+            t.copy_(red)
+        torch.cuda.synchronize()
+
+    for bk, b in zip(bks, bufs):
+        bk.norm_partial1(b.sums, b.mn, b.mx)
+    allreduce("sums"); allreduce("mn", "min"); allreduce("mx", "max")
+    for bk, b in zip(bks, bufs):
+        bk.norm_partial2(b.sums, b.mn, b.mx, b.sq)
+    allreduce("sq")
+    for bk, b in zip(bks, bufs):
+        bk.norm_apply(b.sums, b.mn, b.mx, b.sq)
+        bk.select_begin(total_bases, b.sums)
+    for level in range(8):
+        for bk, b in zip(bks, bufs):
+            bk.select_hist(level, b.hist)
+        allreduce("hist")
+        for bk, b in zip(bks, bufs):
+            bk.select_pick(level, b.hist)
+    for rank, (bk, b) in enumerate(zip(bks, bufs)):
+        bk.select_tie_local(b.tie, rank, world)
+    allreduce("tie")
+    for rank, (bk, b) in enumerate(zip(bks, bufs)):
+        bk.select_apply(b.tie, rank, b.keeping)
+    allreduce("keeping")
+    return [bk.select_summary(b.sums, b.mn, b.mx, b.sq, b.keeping, total_bases) for bk, b in zip(bks, bufs)]
+
+
+@pytest.mark.parametrize("opts,dup", [(dict(keep_percent=60.0), False), (dict(target_bases=250000, min_length=300), False),
+                                      (dict(keep_percent=40.0), True)])
+def test_sharded_split_phase_protocol_on_device(opts, dup):
+    """Two contexts, each holding a contiguous shard of the reads, driven through the split-phase C
+    ABI (fl_norm_* / fl_select_*) with hand-made all-reduces: the union of their pass flags must
+    equal the single-context fl_finalize and the oracle. `dup` repeats reads so that an exact tie
+    class straddles the cut-off AND the shard boundary."""
+    from filtlong_b200 import sharding
+    rng = np.random.default_rng(123)
+    genome = util.rand_seq(rng, 30000)
+    reads = [(s, q) for _, s, q in util.long_reads(rng, genome, 200, max_len=5000)]
+    if dup:
+        reads = reads[:50] * 4
+    p, op = api.make_params(**opts), orc.make_params(**opts)
+    sc = orc.finalize(orc.score(reads, op, None), op)
+    total = sum(len(r[0]) for r in reads)
+    cuts = sharding.shard_by_bases([len(r[0]) for r in reads], 2)
+    ctxs = []
+    for lo, hi in cuts:
+        c = api.Context(p)
+        c.push(api.HostBatch([r[0] for r in reads[lo:hi]], [r[1] for r in reads[lo:hi]], want_seq=False))
+        ctxs.append(c)
+    summaries = _two_shard_finalize(ctxs, total)
+    got = []
+    for c in ctxs:
+        got += [int(x) for x in c.row_results()["passed_final"]]
+    parity.check_selection(got, [r.passed_final for r in sc.rows], [r.final_score for r in sc.rows], [r.length for r in sc.rows])
+    for s in summaries:
+        assert s.status == sc.summary.status
+        if s.status == 3:
+            assert (s.keeping, s.target) == (sc.summary.keeping, sc.summary.target)
+    # and the one-GPU convenience call agrees
+    one, summ = api.score_and_filter(reads, p)
+    assert [int(x) for x in one.row_results()["passed_final"]] == got
+    for c in ctxs + [one]:
+        c.close()
