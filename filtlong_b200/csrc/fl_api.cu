@@ -89,7 +89,6 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (c->d_tfirst) cudaFree(c->d_tfirst);
     if (c->d_bittime) cudaFree(c->d_bittime);
     if (c->d_lut) cudaFree(c->d_lut);
-    if (c->d_utab) cudaFree(c->d_utab);
     if (c->d_buckets) cudaFree(c->d_buckets);
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);

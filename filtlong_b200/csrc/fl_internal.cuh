@@ -117,12 +117,10 @@ struct fl_ctx {
     unsigned long long *d_bittime = nullptr;   // first time each Bloom bit was set
     uint64_t add_counter = 0;                  // global add-stream index (kmers.cpp:109-120 order)
     bool multi_pending = false;
-    unsigned long long *d_count_scratch = nullptr;
 
     // ---- Phred LUTs ----
     double *d_lut = nullptr;   // [0..256) q, [256..512) a = q / window_size
     unsigned long long tie_binades = 0;     // bit e: some Phred table value ties when added to a sum in [2^e, 2^(e+1))
-    unsigned long long *d_utab = nullptr;   // [256] q * 2^64 as exact integers (~0 = not representable), fl_phred.cu
     int lut_window = -1;
 
     // ---- staging for host batches ----
@@ -142,7 +140,6 @@ struct fl_ctx {
     // ---- per-batch scratch ----
     DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer
     DevVec<uint32_t> sc_order;       // rows in descending-length bucket order
-    DevVec<uint32_t> sc_tiles;       // tile descriptors for the probe kernel
     DevVec<unsigned long long> sc_u64a, sc_u64b, sc_u64c;
     DevVec<uint32_t> sc_u32a;
     DevVec<unsigned long long> sc_scan;   // block sums of fl_exclusive_scan_u64
