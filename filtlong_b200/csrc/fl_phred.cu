@@ -430,6 +430,174 @@ __global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_phred_warp: BOTH chains of a read by one warp, 512 bases per step, exact, coalesced.
+//
+// Same identity as k_phred_mean_long, applied to the window recurrence as well. While w stays in one
+// binade [C, 2C) (C = 2^e) every   w -= a_out; w += a_in   moves it by the table values rounded to the
+// binade's grid, r(a) = (C + a) - C, with no other rounding (IEEE RN, a >= 0, no tie). All r are
+// multiples of ulp(C); as long as every prefix of  -r(a_out,0) +r(a_in,0) -r(a_out,1) ...  stays
+// inside (-C, C) every partial sum in any order is exactly representable, so a warp can take the
+// tile with a scan: lane l walks its 16 steps locally (prefix x, its minima after the subtraction
+// and after the addition, its maximum), an exclusive scan of the lane totals places the lanes, and
+// three warp reductions give the tile's lowest point after a subtraction, lowest and highest point
+// after an addition. The tile is accepted iff  w + lowest >= C  and  w + highest < 2C  (tested with a
+// 2^-30 relative safety margin, which also makes the "everything was exact" argument airtight: had
+// any partial sum left (-C, C) the tested values would miss the thresholds by far more than any
+// rounding error), no table value ties in that binade (host-computed mask) and nothing is NaN
+// (qualities outside [0,1) are NaN in the grid tables). Then  w += total,  best = min(best, w +
+// lowest-after-addition)  are the reference's values. A rejected tile -- w crossing 0.5 or 0.25, a
+// tie, an odd byte -- is walked by lane 0 with the reference's own loop; so is everything before the
+// first 16-byte boundary after the first window. The mean's sum rides along exactly as in
+// k_phred_mean_long.
+// ---------------------------------------------------------------------------------------------
+#define PW_SMEM (2 * 256 * 16 * 8)     // grid tables q x16 and a x16 (lane-private bank pairs) = 64 KiB
+#define PW_TILE 512
+
+__device__ __forceinline__ void serial_both(const uint8_t *__restrict__ q, int lo, int hi, int ws, const double *__restrict__ lut,
+                                            bool do_sum, bool do_win, double &s, double &w, double &best) {
+    for (int j = lo; j < hi; ++j) {
+        const unsigned c = q[j];
+        if (do_sum) s += __ldg(lut + c);                                   // read.cpp:210-211
+        if (do_win) {
+            w -= __ldg(lut + 256 + (unsigned)q[j - ws]);                   // read.cpp:229
+            w += __ldg(lut + 256 + c);                                     // read.cpp:230
+            if (w < best) best = w;                                        // read.cpp:231-232
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 3) k_phred_warp(PhredArgs a, unsigned long long tie_q, unsigned long long tie_a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tq_all = reinterpret_cast<double *>(smem_raw);                 // [256][16]
+    double *ta_all = tq_all + 256 * 16;                                    // [256][16]
+    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const double q = a.lut[i >> 4], v = a.lut[256 + (i >> 4)];
+        tq_all[i] = (q >= 0.0 && q < 1.0) ? q : qnan;
+        ta_all[i] = (v >= 0.0 && v < 1.0) ? v : qnan;
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const double *tq = tq_all + (lane & 15), *ta = ta_all + (lane & 15);
+    const int ws = a.p.window_size;
+    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t it = warp; it < a.n; it += n_warps) {
+        const uint32_t r = a.order[it];
+        const int L = a.len[r];
+        const uint8_t *q = a.qual + a.off[r];
+        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
+        double s = 0.0, w = 0.0, best = 0.0;
+        const int head = L < ws ? L : ws;
+        if (lane == 0) serial_both(q, 0, head, ws, a.lut, true, false, s, w, best);
+        if (L <= ws) {                                                     // read.cpp:217-218
+            if (lane == 0) {
+                const double mean = 100.0 * s / (double)L;
+                write_read(a, r, L, mean, mean);
+            }
+            continue;
+        }
+        int H = (ws + 15) & ~15;
+        if (H > L) H = L;
+        if (lane == 0) {
+            w = s / (double)ws;                                            // read.cpp:223
+            best = w;
+            serial_both(q, ws, H, ws, a.lut, true, true, s, w, best);
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        best = __shfl_sync(0xffffffffu, best, 0);
+        const unsigned osh = (unsigned)((16 - (ws & 15)) & 15);           // (lo - ws) & 15 for every 16-aligned lo
+        for (int j = H; j < L; j += PW_TILE) {
+            const int hi = (j + PW_TILE < L) ? j + PW_TILE : L;
+            const int lo = j + 16 * (int)lane;
+            int nb = hi - lo;
+            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+            uint32_t iw[4] = {0u, 0u, 0u, 0u}, ow[4] = {0u, 0u, 0u, 0u};
+            if (nb > 0) {
+                const uint4 in = __ldg(qv + (lo >> 4));
+                iw[0] = in.x; iw[1] = in.y; iw[2] = in.z; iw[3] = in.w;
+                const int blk = (lo - ws) >> 4;                            // >= 0 because lo >= H >= ws
+                const uint4 oa = __ldg(qv + blk), ob = __ldg(qv + blk + 1);   // blk + 1 <= lo / 16
+                const unsigned sh = (osh & 3u) * 8u;
+                switch (osh >> 2) {
+                    case 0: out_words<0>(oa, ob, sh, ow); break;
+                    case 1: out_words<1>(oa, ob, sh, ow); break;
+                    case 2: out_words<2>(oa, ob, sh, ow); break;
+                    default: out_words<3>(oa, ob, sh, ow); break;
+                }
+            }
+            int es = -5000, ew = -5000;
+            if (s > 0.0 && s < inf) { (void)frexp(s, &es); es -= 1; }
+            if (w > 0.0 && w < inf) { (void)frexp(w, &ew); ew -= 1; }
+            const bool ok_s = es >= 9 && es < 64 && !((tie_q >> es) & 1ull);
+            const bool ok_w = ew <= 0 && ew > -64 && !((tie_a >> (-ew)) & 1ull);
+            const double Cs = ldexp(1.0, ok_s ? es : 0), Cw = ldexp(1.0, ok_w ? ew : 0);
+            double ds = 0.0, x = 0.0, mn_sub = inf, mn_add = inf, mx_add = -inf;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < nb) {
+                    const unsigned ci = byte_of(iw[k >> 2], k & 3), co = byte_of(ow[k >> 2], k & 3);
+                    const double qi = tq[ci * 16], ai = ta[ci * 16], ao = ta[co * 16];
+                    ds += (Cs + qi) - Cs;
+                    x -= (Cw + ao) - Cw;
+                    mn_sub = x < mn_sub ? x : mn_sub;
+                    x += (Cw + ai) - Cw;
+                    mn_add = x < mn_add ? x : mn_add;
+                    mx_add = x > mx_add ? x : mx_add;
+                }
+            }
+            // place the lanes: exclusive scan of the lane totals (exact adds, see header)
+            double incl = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += t;
+            }
+            const double off = incl - x;                                   // exact: both multiples of the grid
+            const double total = __shfl_sync(0xffffffffu, incl, 31);
+            const double g_sub = warp_min_d(off + mn_sub), g_add = warp_min_d(off + mn_add), g_max = warp_max_d(off + mx_add);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            const double margin = 9.313225746154785e-10;                   // 2^-30
+            const bool valid_w = ok_w && (w + g_sub) >= Cw * (1.0 + margin) && (w + g_max) < (Cw + Cw) * (1.0 - margin) &&
+                                 total == total;
+            const bool valid_s = ok_s && (s + ds) < Cs + Cs;              // false for NaN
+            if (valid_w) {
+                const double cand = w + g_add;                             // lowest value after an addition in this tile
+                if (cand < best) best = cand;
+                w += total;
+            }
+            if (valid_s) s += ds;
+            if (!valid_w || !valid_s) {                                    // the reference's own loop for what was rejected
+                if (lane == 0) serial_both(q, j, hi, ws, a.lut, !valid_s, !valid_w, s, w, best);
+                s = __shfl_sync(0xffffffffu, s, 0);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                best = __shfl_sync(0xffffffffu, best, 0);
+            }
+        }
+        if (lane == 0) finish(a, r, L, s, best);
+    }
+}
+
 }  // namespace
 
 static int ensure_lut(fl_ctx *ctx) {
@@ -448,6 +616,15 @@ static int ensure_lut(fl_ctx *ctx) {
             const double scaled = ldexp(q, 52 - e);          // exact
             if (scaled - floor(scaled) == 0.5) ctx->tie_binades |= 1ull << e;
         }
+    // same for the window table a[] and the binades [2^-e, 2^(1-e)) of w (bit e), used by k_phred_warp
+    ctx->tie_binades_a = 0;
+    for (int e = 0; e < 64; ++e)
+        for (int c = 0; c < 256; ++c) {
+            const double v = h[256 + c];
+            if (!(v > 0.0 && v < 1.0)) continue;
+            const double scaled = ldexp(v, 52 + e);          // exact (power-of-two scaling)
+            if (scaled < 9007199254740992.0 && scaled - floor(scaled) == 0.5) ctx->tie_binades_a |= 1ull << e;
+        }
     FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->lut_window = ctx->p.window_size;
     return FL_OK;
@@ -464,6 +641,41 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_TRY(fl_reserve_reads(ctx, ctx->n_reads + n));
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
     const int ws = ctx->p.window_size;
+    if (ctx->phred_mode == 1) {
+        // default: one warp per read, both chains by exact grid arithmetic (k_phred_warp)
+        FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
+        FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
+        PhredArgs a{};
+        a.qual = b.qual; a.off = b.off; a.len = b.len; a.n = b.n;
+        a.lut = ctx->d_lut; a.p = ctx->p;
+        const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+        a.r_len = ctx->r_len.p + rb; a.r_first = ctx->r_first.p + rb; a.r_last = ctx->r_last.p + rb;
+        a.r_nbad = ctx->r_nbad.p + rb; a.r_nchild = ctx->r_nchild.p + rb;
+        a.r_mean = ctx->r_mean.p + rb; a.r_window = ctx->r_window.p + rb; a.r_passed = ctx->r_passed.p + rb;
+        a.r_rowstart = ctx->r_rowstart.p + rb;
+        a.w_parent = ctx->w_parent.p + wb; a.w_start = ctx->w_start.p + wb; a.w_end = ctx->w_end.p + wb;
+        a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
+        a.read_base = rb; a.row_base = wb;
+        a.order = ctx->sc_order.p;
+        static bool warp_attr_set = false;
+        if (!warp_attr_set) {
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
+            warp_attr_set = true;
+        }
+        unsigned blocks = fl_blocks(n * 32, 256);
+        const unsigned cap = (unsigned)ctx->sm_count * 3;
+        if (blocks > cap) blocks = cap;
+        {
+            KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
+            k_phred_warp<<<blocks, 256, PW_SMEM, st>>>(a, ctx->tie_binades, ctx->tie_binades_a);
+        }
+        ctx->launches++;
+        FL_CUDA(ctx, cudaGetLastError());
+        ctx->n_reads += n;
+        ctx->n_rows += n;
+        return FL_OK;
+    }
+    // ---- phred_mode 0 (kept for comparison): work items, one thread per chain ----
     // ---- plan: items per read -> exclusive scan -> item table ----
     FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, st));
     k_phred_plan<<<fl_blocks(n, 256), 256, 0, st>>>(b.len, b.n, ws, ctx->sc_u64a.p);
