@@ -65,6 +65,7 @@ struct PhredArgs {
     unsigned long long n_items;
     double *it_a, *it_b, *it_c;             // per item: MEAN: sum | SEG: entry, exit, best
     uint32_t *fallback;                     // [0] = count, [1..] = reads to re-score serially
+    int head_len;                           // k_phred_head / k_phred_warp: bases walked by the per-read head pass
 };
 
 __device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
@@ -430,6 +431,34 @@ __global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws
     }
 }
 
+// k_phred_head: the first head_len bases of every read, one thread per read (the reference's loop
+// verbatim). The running sum is tiny there -- it climbs through a new binade every few bases, where
+// table values tie and tiles cannot be big -- so the warp kernel takes over only after head_len
+// bases; 32 reads per warp walking equally long heads keep the lanes busy. Reads not longer than
+// head_len are finished here.
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_head(PhredArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Tab t = make_tables(a.lut, smem_raw);
+    const int ws = a.p.window_size;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (size_t)gridDim.x * blockDim.x) {
+        const int L = a.len[r];
+        const uint8_t *q = a.qual + a.off[r];
+        const int lim = L < a.head_len ? L : a.head_len;
+        double sum = 0.0, w = 0.0, best = 0.0;
+        chain<true, false>(q, 0, lim < ws ? lim : ws, ws, t, sum, w, best);
+        if (L <= ws) {                                   // read.cpp:217-218
+            const double mean = 100.0 * sum / (double)L;
+            write_read(a, (uint32_t)r, L, mean, mean);
+            continue;
+        }
+        w = sum / (double)ws;                            // read.cpp:223
+        best = w;
+        chain<true, true>(q, ws, lim, ws, t, sum, w, best);
+        if (L <= a.head_len) finish(a, (uint32_t)r, L, sum, best);
+        else { a.it_a[r] = sum; a.it_b[r] = w; a.it_c[r] = best; }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_phred_warp: BOTH chains of a read by one warp, 512 bases per step, exact, coalesced.
 //
@@ -505,26 +534,10 @@ __global__ void __launch_bounds__(256, 3) k_phred_warp(PhredArgs a, unsigned lon
         const int L = a.len[r];
         const uint8_t *q = a.qual + a.off[r];
         const uint4 *qv = reinterpret_cast<const uint4 *>(q);
-        double s = 0.0, w = 0.0, best = 0.0;
-        const int head = L < ws ? L : ws;
-        if (lane == 0) serial_both(q, 0, head, ws, a.lut, true, false, s, w, best);
-        if (L <= ws) {                                                     // read.cpp:217-218
-            if (lane == 0) {
-                const double mean = 100.0 * s / (double)L;
-                write_read(a, r, L, mean, mean);
-            }
-            continue;
-        }
-        int H = (ws + 15) & ~15;
-        if (H > L) H = L;
-        if (lane == 0) {
-            w = s / (double)ws;                                            // read.cpp:223
-            best = w;
-            serial_both(q, ws, H, ws, a.lut, true, true, s, w, best);
-        }
-        s = __shfl_sync(0xffffffffu, s, 0);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        best = __shfl_sync(0xffffffffu, best, 0);
+        if (L <= a.head_len) continue;                                 // finished by k_phred_head
+        // state after the first head_len bases (k_phred_head): running sum, window value, minimum
+        double s = a.it_a[r], w = a.it_b[r], best = a.it_c[r];
+        const int H = a.head_len;                                          // multiple of 16, > ws
         const unsigned osh = (unsigned)((16 - (ws & 15)) & 15);           // (lo - ws) & 15 for every 16-aligned lo
         for (int j = H; j < L; j += PW_TILE) {
             const int hi = (j + PW_TILE < L) ? j + PW_TILE : L;
@@ -657,10 +670,20 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
         a.read_base = rb; a.row_base = wb;
         a.order = ctx->sc_order.p;
+        a.head_len = ((ws + 15) & ~15) + 768;           // > ws, multiple of 16, sum has reached 2^9 by then
+        FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n + 8, 0, st));
+        a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n; a.it_c = ctx->sc_f64.p + 2 * n;
         static bool warp_attr_set = false;
         if (!warp_attr_set) {
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_head, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             warp_attr_set = true;
+        }
+        {
+            unsigned hb = fl_blocks(n, PH_THREADS);
+            if (hb > (unsigned)ctx->sm_count * 3) hb = (unsigned)ctx->sm_count * 3;
+            k_phred_head<<<hb, PH_THREADS, PH_SMEM, st>>>(a);
+            ctx->launches++;
         }
         unsigned blocks = fl_blocks(n * 32, 256);
         const unsigned cap = (unsigned)ctx->sm_count * 3;
