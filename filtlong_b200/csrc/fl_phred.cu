@@ -65,7 +65,7 @@ struct PhredArgs {
     unsigned long long n_items;
     double *it_a, *it_b, *it_c;             // per item: MEAN: sum | SEG: entry, exit, best
     uint32_t *fallback;                     // [0] = count, [1..] = reads to re-score serially
-    int head_len;                           // k_phred_head / k_phred_warp: bases walked by the per-read head pass
+    int head_len;                           // k_phred_head: bases walked by the per-read head pass
 };
 
 __device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
@@ -460,154 +460,304 @@ __global__ void __launch_bounds__(PH_THREADS, 3) k_phred_head(PhredArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_phred_warp: BOTH chains of a read by one warp, 512 bases per step, exact, coalesced.
+// k_phred_tile: BOTH chains of a read by one warp, one window length (ws bases) per step, exact.
 //
-// Same identity as k_phred_mean_long, applied to the window recurrence as well. While w stays in one
-// binade [C, 2C) (C = 2^e) every   w -= a_out; w += a_in   moves it by the table values rounded to the
-// binade's grid, r(a) = (C + a) - C, with no other rounding (IEEE RN, a >= 0, no tie). All r are
-// multiples of ulp(C); as long as every prefix of  -r(a_out,0) +r(a_in,0) -r(a_out,1) ...  stays
-// inside (-C, C) every partial sum in any order is exactly representable, so a warp can take the
-// tile with a scan: lane l walks its 16 steps locally (prefix x, its minima after the subtraction
-// and after the addition, its maximum), an exclusive scan of the lane totals places the lanes, and
-// three warp reductions give the tile's lowest point after a subtraction, lowest and highest point
-// after an addition. The tile is accepted iff  w + lowest >= C  and  w + highest < 2C  (tested with a
-// 2^-30 relative safety margin, which also makes the "everything was exact" argument airtight: had
-// any partial sum left (-C, C) the tested values would miss the thresholds by far more than any
-// rounding error), no table value ties in that binade (host-computed mask) and nothing is NaN
-// (qualities outside [0,1) are NaN in the grid tables). Then  w += total,  best = min(best, w +
-// lowest-after-addition)  are the reference's values. A rejected tile -- w crossing 0.5 or 0.25, a
-// tie, an odd byte -- is walked by lane 0 with the reference's own loop; so is everything before the
-// first 16-byte boundary after the first window. The mean's sum rides along exactly as in
-// k_phred_mean_long.
+// Lattice identity (as in k_phred_mean_long): while a running double v stays inside one binade
+// [C, 2C) it is a multiple of u = ulp(C), and for 0 <= t < C (IEEE RN, t not exactly half way between
+// two multiples of u)      fl(v + t) = v + r(t),   fl(v - t) = v - r(t),   r(t) = t rounded to the grid u.
+// So the chain is a sum of grid steps, exact in ANY order as long as every partial sum stays inside
+// the binade -- and the rounding r() itself is done by the adder: a lane that walks its bases from an
+// ANCHOR inside the same binade (1.5 C for the window chain, C for the mean's sum) gets exactly the
+// same grid steps as the reference's chain does from its own value.
+//
+// Layout: step t covers bases [ws + t ws, ws + (t+1) ws); lane l owns K = ceil(ws/32) consecutive
+// bases of it, ALWAYS the same offsets, so the value that leaves the window when lane l adds its
+// k-th base is the value lane l added at its k-th base one step earlier: it is still in a register.
+// Per base: one 16-byte shared-memory gather {q[c], a[c]} (8 lane-private copies, conflict free), one
+// add for the sum, subtract + add + compare for the window.
+//   window: the lane walks x = 0.75 - old_k + new_k ..., keeps its lowest point and its total; one
+//     warp scan of the totals places the lanes (exact: grid multiples), so the absolute running
+//     minimum is min over lanes of (W + prefix + lowest point). The whole read is assumed to keep w
+//     inside [0.5, 1): upper side by construction (every table value is below (1 - 1e-10)/ws, the
+//     first window W0 = fl(sum/ws) is within 1e-13 of the grid sum of its own values, so every later
+//     grid value is below 1 - 4e-10), lower side CHECKED at the end: minimum - max table value >= 0.5
+//     (the lowest point after a subtraction is at most one table value below a point after an
+//     addition). Table values that tie on the grid 2^-53, or lie outside [0, 1), are NaN in the warp's
+//     table: NaN reaches W and the read is rejected. A rejected read goes to k_phred_fallback (the
+//     reference's loop verbatim, one thread).
+//   sum: lane-local acc = C + q + q + ... (C = 2^e, the binade of the running sum s): exact grid steps
+//     while acc < 2C, collected only when the room left in the binade (2C - s, each step adds < 1)
+//     could run out: O(log) warp reductions per binade. The step in which s may cross into the next
+//     binade ("careful" step) is resolved exactly: scan of the lanes' chunk sums, first lane whose
+//     prefix reaches 2C walks its K bases with true adds, the lanes after it redo their chunks on the
+//     coarser grid. Binades in which some table value would tie (host mask; only s < 1024 for the
+//     Phred table) run every step careful with a per-base tie test; a tie, a NaN or anything
+//     unexpected sends that one step to lane 0 and the reference's own loop.
 // ---------------------------------------------------------------------------------------------
-#define PW_SMEM (2 * 256 * 16 * 8)     // grid tables q x16 and a x16 (lane-private bank pairs) = 64 KiB
-#define PW_TILE 512
+#define PT_THREADS 256
+#define PT_SMEM (256 * 8 * 16)         // {q, a} x 8 lane-private copies = 32 KiB
 
-__device__ __forceinline__ void serial_both(const uint8_t *__restrict__ q, int lo, int hi, int ws, const double *__restrict__ lut,
-                                            bool do_sum, bool do_win, double &s, double &w, double &best) {
-    for (int j = lo; j < hi; ++j) {
-        const unsigned c = q[j];
-        if (do_sum) s += __ldg(lut + c);                                   // read.cpp:210-211
-        if (do_win) {
-            w -= __ldg(lut + 256 + (unsigned)q[j - ws]);                   // read.cpp:229
-            w += __ldg(lut + 256 + c);                                     // read.cpp:230
-            if (w < best) best = w;                                        // read.cpp:231-232
+__device__ __forceinline__ int exponent_of(double v) { return (int)((__double2hiint(v) >> 20) & 0x7FF) - 1023; }
+__device__ __forceinline__ double pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double warp_incl_scan(double v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ long long warp_incl_scan_ll(long long v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// table entry of the k-th byte of a chunk: tl + 128 * byte
+__device__ __forceinline__ const double2 *entry_of(const double2 *tl, uint32_t w, int k) {
+    const uint32_t c = __byte_perm(w, 0u, 0x4440u + (unsigned)k);
+    return reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(tl) + (c << 7));
+}
+
+// the K bytes at byte position pos of a read (any alignment), as ceil(K/4) words
+template <int NW>
+__device__ __forceinline__ void load_chunk(const uint32_t *__restrict__ q32, int pos, int maxword, uint32_t (&o)[NW]) {
+    const int wi = pos >> 2;
+    const unsigned bs = ((unsigned)pos & 3u) * 8u;
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; ++i) {
+        const int x = wi + i;
+        w[i] = __ldg(q32 + (x < maxword ? x : maxword));
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], bs);
+}
+
+#define PT_ANCHOR 0.75
+#define PT_ANCHOR_BITS 0x3FE8000000000000ll
+
+// one step of one lane: K bases; TAIL: only the first nvalid bases exist. x ends at anchor + (sum of the
+// lane's grid steps), m is its lowest point after an addition (the anchor itself if the lane owns nothing).
+template <int K, bool TAIL>
+__device__ __forceinline__ void tile_core(const uint32_t (&cw)[(K + 3) / 4], const double2 *__restrict__ tl, int nvalid,
+                                          double (&old)[K], double &acc, double &x, double &m) {
+    x = PT_ANCHOR;
+    m = PT_ANCHOR;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double2 e = *entry_of(tl, cw[k >> 2], k & 3);
+        if (!TAIL || k < nvalid) {
+            acc += e.x;                    // read.cpp:210-211 on the grid of the sum's binade
+            x -= old[k];                   // read.cpp:229
+            x += e.y;                      // read.cpp:230
+            m = x < m ? x : m;             // read.cpp:231-232
+            old[k] = e.y;
         }
     }
 }
 
-__device__ __forceinline__ double warp_min_d(double v) {
+// chunk sum of one lane on the grid of [C, 2C), optional tie test
+template <int K>
+__device__ __forceinline__ double chunk_sum(const uint32_t (&cw)[(K + 3) / 4], const double2 *__restrict__ tl, int nvalid, double C,
+                                            bool check, bool &bad) {
+    double acc = C;
+    const double half = C * 1.1102230246251565e-16;   // ulp(C) / 2 = C * 2^-53
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t < v ? t : v;
+    for (int k = 0; k < K; ++k) {
+        if (k < nvalid) {
+            const double q = entry_of(tl, cw[k >> 2], k & 3)->x;
+            if (check) {
+                const double r = (C + q) - C;
+                bad |= fabs(q - r) == half;           // q - r is exact
+            }
+            acc += q;
+        }
     }
-    return v;
-}
-__device__ __forceinline__ double warp_max_d(double v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t > v ? t : v;
-    }
-    return v;
+    return acc - C;
 }
 
-__global__ void __launch_bounds__(256, 3) k_phred_warp(PhredArgs a, unsigned long long tie_q, unsigned long long tie_a) {
+template <int K>
+__global__ void __launch_bounds__(PT_THREADS, 3) k_phred_tile(PhredArgs a, unsigned long long tie_q) {
+    constexpr int NW = (K + 3) / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *tq_all = reinterpret_cast<double *>(smem_raw);                 // [256][16]
-    double *ta_all = tq_all + 256 * 16;                                    // [256][16]
+    double2 *tab = reinterpret_cast<double2 *>(smem_raw);              // [256][8]
+    __shared__ double s_amax;
+    const int ws = a.p.window_size;
     const double qnan = __longlong_as_double(0x7FF8000000000000ll);
-    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-        const double q = a.lut[i >> 4], v = a.lut[256 + (i >> 4)];
-        tq_all[i] = (q >= 0.0 && q < 1.0) ? q : qnan;
-        ta_all[i] = (v >= 0.0 && v < 1.0) ? v : qnan;
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int c = 0; c < 256; ++c) {
+            const double v = a.lut[256 + c];
+            if (v >= 0.0 && v > mx && v * (double)ws <= 1.0 - 1e-10) mx = v;
+        }
+        s_amax = mx;
+    }
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        const int c = i >> 3;
+        double q = a.lut[c], v = a.lut[256 + c];
+        if (!(q >= 0.0 && q < 1.0)) q = qnan;
+        bool ok = v >= 0.0 && v * (double)ws <= 1.0 - 1e-10;
+        if (ok && v > 0.0) {
+            const double sc = ldexp(v, 53);                           // exact; v < 1 so sc < 2^53
+            ok = (sc - floor(sc)) != 0.5;                              // would tie on the grid of [0.5, 1)
+        }
+        if (!ok) v = qnan;
+        tab[i] = make_double2(q, v);
     }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const double *tq = tq_all + (lane & 15), *ta = ta_all + (lane & 15);
-    const int ws = a.p.window_size;
-    const double inf = __longlong_as_double(0x7FF0000000000000ll);
+    const double2 *tl = tab + (lane & 7);
+    const double thr = 0.5 + s_amax;
+    const double wsd = (double)ws;
+    const int nb_lane = max(0, min(K, ws - K * (int)lane));          // bases of a full step owned by this lane
+    // bytes beyond the lane's share read as '!' (q = a = 0: no effect on either chain)
+    uint32_t keep[NW], fill[NW];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (4 * i + b < nb_lane) m |= 0xFFu << (8 * b);
+        keep[i] = m;
+        fill[i] = 0x21212121u & ~m;
+    }
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t it = warp; it < a.n; it += n_warps) {
         const uint32_t r = a.order[it];
         const int L = a.len[r];
+        if (L <= ws) continue;                                         // finished by k_phred_head
         const uint8_t *q = a.qual + a.off[r];
-        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
-        if (L <= a.head_len) continue;                                 // finished by k_phred_head
-        // state after the first head_len bases (k_phred_head): running sum, window value, minimum
-        double s = a.it_a[r], w = a.it_b[r], best = a.it_c[r];
-        const int H = a.head_len;                                          // multiple of 16, > ws
-        const unsigned osh = (unsigned)((16 - (ws & 15)) & 15);           // (lo - ws) & 15 for every 16-aligned lo
-        for (int j = H; j < L; j += PW_TILE) {
-            const int hi = (j + PW_TILE < L) ? j + PW_TILE : L;
-            const int lo = j + 16 * (int)lane;
-            int nb = hi - lo;
-            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-            uint32_t iw[4] = {0u, 0u, 0u, 0u}, ow[4] = {0u, 0u, 0u, 0u};
-            if (nb > 0) {
-                const uint4 in = __ldg(qv + (lo >> 4));
-                iw[0] = in.x; iw[1] = in.y; iw[2] = in.z; iw[3] = in.w;
-                const int blk = (lo - ws) >> 4;                            // >= 0 because lo >= H >= ws
-                const uint4 oa = __ldg(qv + blk), ob = __ldg(qv + blk + 1);   // blk + 1 <= lo / 16
-                const unsigned sh = (osh & 3u) * 8u;
-                switch (osh >> 2) {
-                    case 0: out_words<0>(oa, ob, sh, ow); break;
-                    case 1: out_words<1>(oa, ob, sh, ow); break;
-                    case 2: out_words<2>(oa, ob, sh, ow); break;
-                    default: out_words<3>(oa, ob, sh, ow); break;
+        const uint32_t *q32 = reinterpret_cast<const uint32_t *>(q);
+        const int maxword = (((L + 63) & ~63) >> 2) - 1;
+        double s = a.it_a[r];                                          // sum of the first window (k_phred_head)
+        const double W0 = a.it_b[r];                                   // fl(sum / ws), read.cpp:223
+        bool reject = !(W0 >= thr && W0 < 1.0);
+        // the window chain as bit patterns: inside [0.5, 1) one grid step is one unit of the pattern
+        long long Wb = __double_as_longlong(W0), mnb = Wb;
+        bool nanf = false;
+        double old[K];
+        {
+            uint32_t cw[NW];
+            load_chunk<NW>(q32, K * (int)lane, maxword, cw);
+#pragma unroll
+            for (int k = 0; k < K; ++k) old[k] = (k < nb_lane) ? entry_of(tl, cw[k >> 2], k & 3)->y : 0.0;
+        }
+        int e = exponent_of(s);
+        double Cs = pow2(e);
+        double acc = Cs;
+        int budget = 0;                                                // steps the sum may still take on the lane-local grid
+        uint32_t pre[NW];
+        if (!reject) load_chunk<NW>(q32, ws + K * (int)lane, maxword, pre);
+        for (int j = ws; j < L && !reject; j += ws) {
+            uint32_t cw[NW];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) cw[i] = pre[i];
+            if (j + ws < L) load_chunk<NW>(q32, j + ws + K * (int)lane, maxword, pre);
+            const int n = (L - j < ws) ? L - j : ws;
+            // ---- mean: may this step run on the lane-local grid? ----
+            if (budget == 0) {
+                s += warp_sum(acc - Cs);                               // exact, still below 2 Cs
+                acc = Cs;
+                if (e >= 5 && e < 62 && !((tie_q >> e) & 1ull)) {
+                    const double room = (Cs + Cs) - s;                 // every base adds at most 1
+                    budget = __double2int_rd(fmin(room / wsd, 1.0e6)) - 1;
+                    if (budget < 0) budget = 0;
                 }
             }
-            int es = -5000, ew = -5000;
-            if (s > 0.0 && s < inf) { (void)frexp(s, &es); es -= 1; }
-            if (w > 0.0 && w < inf) { (void)frexp(w, &ew); ew -= 1; }
-            const bool ok_s = es >= 9 && es < 64 && !((tie_q >> es) & 1ull);
-            const bool ok_w = ew <= 0 && ew > -64 && !((tie_a >> (-ew)) & 1ull);
-            const double Cs = ldexp(1.0, ok_s ? es : 0), Cw = ldexp(1.0, ok_w ? ew : 0);
-            double ds = 0.0, x = 0.0, mn_sub = inf, mn_add = inf, mx_add = -inf;
+            const bool fast = budget > 0;
+            double x, m;
+            int nvalid = nb_lane;
+            if (n == ws) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < nb) {
-                    const unsigned ci = byte_of(iw[k >> 2], k & 3), co = byte_of(ow[k >> 2], k & 3);
-                    const double qi = tq[ci * 16], ai = ta[ci * 16], ao = ta[co * 16];
-                    ds += (Cs + qi) - Cs;
-                    x -= (Cw + ao) - Cw;
-                    mn_sub = x < mn_sub ? x : mn_sub;
-                    x += (Cw + ai) - Cw;
-                    mn_add = x < mn_add ? x : mn_add;
-                    mx_add = x > mx_add ? x : mx_add;
+                for (int i = 0; i < NW; ++i) cw[i] = (cw[i] & keep[i]) | fill[i];
+                tile_core<K, false>(cw, tl, K, old, acc, x, m);
+            } else {
+                nvalid = max(0, min(nb_lane, n - K * (int)lane));
+                tile_core<K, true>(cw, tl, nvalid, old, acc, x, m);
+            }
+            // ---- window: place the lanes (integer scan of the grid steps) ----
+            nanf |= (x != x);
+            const long long nx = __double_as_longlong(x) - PT_ANCHOR_BITS;
+            const long long inc = warp_incl_scan_ll(nx, lane);
+            const long long cand = Wb + (inc - nx) + (__double_as_longlong(m) - PT_ANCHOR_BITS);   // lowest point of this lane
+            mnb = cand < mnb ? cand : mnb;
+            Wb += __shfl_sync(0xffffffffu, inc, 31);
+            // ---- mean ----
+            if (fast) {
+                --budget;
+            } else {
+                bool ser = !(e >= 5 && e < 62) || !(s > 0.0);
+                if (!ser) {
+                    bool bad = false;
+                    const double cs = chunk_sum<K>(cw, tl, nvalid, Cs, (tie_q >> e) & 1ull, bad);
+                    const double P = warp_incl_scan(cs, lane);
+                    const double Pall = shfl_d(P, 31);
+                    if (__any_sync(0xffffffffu, bad) || !(Pall == Pall)) {
+                        ser = true;
+                    } else {
+                        const unsigned cross = __ballot_sync(0xffffffffu, s + P >= Cs + Cs);
+                        if (cross == 0u) {
+                            s += Pall;
+                        } else {
+                            const int lx = __ffs(cross) - 1;
+                            double t = s + shfl_d(P - cs, lx);         // exact sum before lane lx's chunk
+                            if ((int)lane == lx) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k)
+                                    if (k < nvalid) t += entry_of(tl, cw[k >> 2], k & 3)->x;   // true adds (read.cpp:210-211)
+                            }
+                            t = shfl_d(t, lx);
+                            const double C2 = Cs + Cs;
+                            bool bad2 = false;
+                            const double cs2 = chunk_sum<K>(cw, tl, (int)lane > lx ? nvalid : 0, C2, (tie_q >> (e + 1)) & 1ull, bad2);
+                            const double rest = warp_sum(cs2);
+                            if (exponent_of(t) != e + 1 || __any_sync(0xffffffffu, bad2) || !(t + rest < C2 + C2)) {
+                                ser = true;
+                            } else {
+                                s = t + rest;
+                                e += 1;
+                                Cs = C2;
+                            }
+                        }
+                    }
                 }
-            }
-            // place the lanes: exclusive scan of the lane totals (exact adds, see header)
-            double incl = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (unsigned)d) incl += t;
-            }
-            const double off = incl - x;                                   // exact: both multiples of the grid
-            const double total = __shfl_sync(0xffffffffu, incl, 31);
-            const double g_sub = warp_min_d(off + mn_sub), g_add = warp_min_d(off + mn_add), g_max = warp_max_d(off + mx_add);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
-            const double margin = 9.313225746154785e-10;                   // 2^-30
-            const bool valid_w = ok_w && (w + g_sub) >= Cw * (1.0 + margin) && (w + g_max) < (Cw + Cw) * (1.0 - margin) &&
-                                 total == total;
-            const bool valid_s = ok_s && (s + ds) < Cs + Cs;              // false for NaN
-            if (valid_w) {
-                const double cand = w + g_add;                             // lowest value after an addition in this tile
-                if (cand < best) best = cand;
-                w += total;
-            }
-            if (valid_s) s += ds;
-            if (!valid_w || !valid_s) {                                    // the reference's own loop for what was rejected
-                if (lane == 0) serial_both(q, j, hi, ws, a.lut, !valid_s, !valid_w, s, w, best);
-                s = __shfl_sync(0xffffffffu, s, 0);
-                w = __shfl_sync(0xffffffffu, w, 0);
-                best = __shfl_sync(0xffffffffu, best, 0);
+                if (ser) {                                             // the reference's own loop for this step
+                    if (lane == 0)
+                        for (int p = 0; p < n; ++p) s += __ldg(a.lut + (unsigned)q[j + p]);
+                    s = shfl_d(s, 0);
+                    e = exponent_of(s);
+                    Cs = pow2(e);
+                }
+                acc = Cs;
+                budget = 0;
             }
         }
-        if (lane == 0) finish(a, r, L, s, best);
+        double mn = 0.0;
+        if (!reject) {
+            s += warp_sum(acc - Cs);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const long long t = __shfl_xor_sync(0xffffffffu, mnb, o);
+                mnb = t < mnb ? t : mnb;
+            }
+            mn = __longlong_as_double(mnb);
+            reject = __any_sync(0xffffffffu, nanf) || !(mn >= thr) || !(s == s);
+        }
+        if (lane == 0) {
+            if (reject) a.fallback[1 + atomicAdd(a.fallback, 1u)] = r;
+            else finish(a, r, L, s, mn);
+        }
     }
 }
 
@@ -629,7 +779,7 @@ static int ensure_lut(fl_ctx *ctx) {
             const double scaled = ldexp(q, 52 - e);          // exact
             if (scaled - floor(scaled) == 0.5) ctx->tie_binades |= 1ull << e;
         }
-    // same for the window table a[] and the binades [2^-e, 2^(1-e)) of w (bit e), used by k_phred_warp
+    // same for the window table a[] and the binades [2^-e, 2^(1-e)) of w (bit e), (kept for diagnostics)
     ctx->tie_binades_a = 0;
     for (int e = 0; e < 64; ++e)
         for (int c = 0; c < 256; ++c) {
@@ -654,8 +804,8 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_TRY(fl_reserve_reads(ctx, ctx->n_reads + n));
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
     const int ws = ctx->p.window_size;
-    if (ctx->phred_mode == 1) {
-        // default: one warp per read, both chains by exact grid arithmetic (k_phred_warp)
+    if (ctx->phred_mode == 1 && ws >= 16 && ws <= 256) {
+        // default: one warp per read, both chains by exact grid arithmetic (k_phred_tile)
         FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
         FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
         PhredArgs a{};
@@ -670,14 +820,20 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
         a.read_base = rb; a.row_base = wb;
         a.order = ctx->sc_order.p;
-        a.head_len = ((ws + 15) & ~15) + 768;           // > ws, multiple of 16, sum has reached 2^9 by then
+        a.head_len = ws;                                  // k_phred_head: the first window, and reads not longer than it
         FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n + 8, 0, st));
         a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n; a.it_c = ctx->sc_f64.p + 2 * n;
-        static bool warp_attr_set = false;
-        if (!warp_attr_set) {
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, PW_SMEM));
+        FL_CUDA(ctx, ctx->sc_u32a.reserve(n + 2, 0, st));
+        a.fallback = ctx->sc_u32a.p;
+        FL_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, sizeof(uint32_t), st));
+        static bool tile_attr_set = false;
+        if (!tile_attr_set) {
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_head, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
-            warp_attr_set = true;
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+            tile_attr_set = true;
         }
         {
             unsigned hb = fl_blocks(n, PH_THREADS);
@@ -685,13 +841,17 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
             k_phred_head<<<hb, PH_THREADS, PH_SMEM, st>>>(a);
             ctx->launches++;
         }
-        unsigned blocks = fl_blocks(n * 32, 256);
-        const unsigned cap = (unsigned)ctx->sm_count * 3;
+        unsigned blocks = fl_blocks(n * 32, PT_THREADS);
+        const unsigned cap = (unsigned)ctx->sm_count * 4;
         if (blocks > cap) blocks = cap;
         {
             KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
-            k_phred_warp<<<blocks, 256, PW_SMEM, st>>>(a, ctx->tie_binades, ctx->tie_binades_a);
+            if (ws <= 64) k_phred_tile<2><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
+            else if (ws <= 128) k_phred_tile<4><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
+            else k_phred_tile<8><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
         }
+        ctx->launches++;
+        k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);   // reads the warp kernel rejected (normally none)
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
         ctx->n_reads += n;

@@ -105,6 +105,49 @@ def test_phred_long_read_segment_prediction_and_fallback(ws):
     ctx.close()
 
 
+@pytest.mark.parametrize("ws", [250, 16, 33, 64, 65, 128, 129, 200, 256, 257])
+def test_phred_tile_kernel_edges(ws):
+    """k_phred_tile (one warp per read, one window length per step): read lengths around multiples of
+    the window, every chunk width (window sizes 16..256; 257 takes the work-item kernels), sums that
+    cross binades inside a step, qualities whose window stays near 1.0 (Q40+, PacBio '~'), near and
+    below 0.5 (rejected -> serial kernel), tie-prone window sizes (200: Q9 ties on the 2^-53 grid),
+    all-'!' reads (sum stays 0) and bytes outside the Phred range."""
+    rng = np.random.default_rng(1000 + ws)
+    reads = []
+    for L in [ws + 1, ws + 2, 2 * ws - 1, 2 * ws, 2 * ws + 1, 3 * ws, 5 * ws + 7, 9 * ws - 1, 33 * ws + 3, 1023, 1024, 1025,
+              2047, 2048, 2049, 4100, 8200, 16390, 40000]:
+        if L > ws:
+            reads.append((b"A" * L, util.rand_qual(rng, L, mean_q=rng.uniform(5, 30))))
+    reads.append((b"A" * 30000, util.rand_qual(rng, 30000, mean_q=45, sd=3, hi=60)))          # w ~ 0.9999
+    reads.append((b"A" * 25000, b"~" * 25000))                                                 # Q93 everywhere
+    reads.append((b"A" * 25000, bytes(rng.choice(np.frombuffer(b"~}|{", np.uint8), size=25000))))
+    reads.append((b"A" * 20000, util.rand_qual(rng, 20000, mean_q=3.2, sd=1.5)))              # w around 0.5
+    reads.append((b"A" * 20000, util.rand_qual(rng, 20000, mean_q=2, sd=1)))                  # w below 0.5
+    # (no all-'!' read: next to the invalid-byte reads below its score would be NaN among finite ones)
+    reads.append((b"A" * 9000, b"!" * 4000 + b"I" * 5000))                                     # q = 0: the sum stays 0 for 16 steps
+    reads.append((b"A" * 12000, b"I" * 6000 + b"!" * 300 + b"I" * 5700))                       # window dips to 0
+    reads.append((b"A" * 12000, util.rand_qual(rng, 6000, mean_q=20) + bytes([200]) + util.rand_qual(rng, 5999, mean_q=20)))
+    reads.append((b"A" * 12000, util.rand_qual(rng, 6000, mean_q=20) + bytes([12]) + util.rand_qual(rng, 5999, mean_q=20)))
+    reads.append((b"A" * 7000, bytes(rng.integers(33 + 40, 33 + 50, size=7000).astype(np.uint8))))   # Q44 ties while the sum is in [512, 1024)
+    reads.append((b"A" * 7000, bytes(rng.integers(33 + 75, 33 + 93, size=7000).astype(np.uint8))))   # Q79 / Q89 tie in [128, 512)
+    reads.append((b"A" * 150000, util.rand_qual(rng, 150000, mean_q=17)))
+    ctx, summ, sc, _ = run_both(reads, dict(keep_percent=70.0, window_size=ws))
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
+def test_phred_tile_kernel_many_reads():
+    """A few thousand ordinary reads (default window): every warp of the grid takes several reads."""
+    rng = np.random.default_rng(77)
+    reads = []
+    for _ in range(3000):
+        L = int(np.clip(rng.lognormal(7.5, 1.0), 20, 60000))
+        reads.append((b"A" * L, util.rand_qual(rng, L, mean_q=float(np.clip(rng.normal(14, 4), 5, 30)))))
+    ctx, summ, sc, _ = run_both(reads, dict(target_bases=3000000))
+    full_check(ctx, summ, sc)
+    ctx.close()
+
+
 def make_kmer_case(seed, n_reads=150, genome_len=60000, max_len=9000):
     rng = np.random.default_rng(seed)
     genome = util.rand_seq(rng, genome_len)
