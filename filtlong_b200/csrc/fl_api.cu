@@ -60,6 +60,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
     if (const char *f = getenv("FL_PHRED_MODE")) c->phred_mode = atoi(f);
+    if (const char *f = getenv("FL_PHRED_OCC")) c->phred_occupancy = atoi(f);
     {
         const char *pe = getenv("FL_L2_PERSIST");
         if (pe && atoi(pe) != 0) {   // off by default: measured slower (the set-aside shrinks the normal L2)

@@ -121,8 +121,11 @@ struct fl_ctx {
     // ---- Phred LUTs ----
     double *d_lut = nullptr;   // [0..256) q, [256..512) a = q / window_size
     unsigned long long tie_binades = 0;     // bit e: some Phred table value ties when added to a sum in [2^e, 2^(e+1))
+    unsigned long long tie_many = 0;        // bit e: more than one table value ties there
+    unsigned char tie_char[64] = {0};       // the one that does, when exactly one
     unsigned long long tie_binades_a = 0;   // bit e: some window-table value ties when w is in [2^-e, 2^(1-e))
-    int phred_mode = 1;                     // 1: k_phred_warp (default); 0: work-item kernels (FL_PHRED_MODE)
+    int phred_mode = 1;                     // 1: k_phred_sum + k_phred_win (default); 0: work-item kernels (FL_PHRED_MODE)
+    int phred_occupancy = 4;                // blocks per SM launched for k_phred_sum / k_phred_win (FL_PHRED_OCC)
     int lut_window = -1;
 
     // ---- staging for host batches ----

@@ -65,7 +65,7 @@ struct PhredArgs {
     unsigned long long n_items;
     double *it_a, *it_b, *it_c;             // per item: MEAN: sum | SEG: entry, exit, best
     uint32_t *fallback;                     // [0] = count, [1..] = reads to re-score serially
-    int head_len;                           // k_phred_head: bases walked by the per-read head pass
+    int head_len;                           // k_phred_first: bases whose sum the per-read first pass takes
 };
 
 __device__ __forceinline__ unsigned byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
@@ -431,84 +431,60 @@ __global__ void k_phred_fill(const int32_t *__restrict__ len, uint32_t n, int ws
     }
 }
 
-// k_phred_head: the first head_len bases of every read, one thread per read (the reference's loop
-// verbatim). The running sum is tiny there -- it climbs through a new binade every few bases, where
-// table values tie and tiles cannot be big -- so the warp kernel takes over only after head_len
-// bases; 32 reads per warp walking equally long heads keep the lanes busy. Reads not longer than
-// head_len are finished here.
-__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_head(PhredArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Tab t = make_tables(a.lut, smem_raw);
-    const int ws = a.p.window_size;
-    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (size_t)gridDim.x * blockDim.x) {
-        const int L = a.len[r];
-        const uint8_t *q = a.qual + a.off[r];
-        const int lim = L < a.head_len ? L : a.head_len;
-        double sum = 0.0, w = 0.0, best = 0.0;
-        chain<true, false>(q, 0, lim < ws ? lim : ws, ws, t, sum, w, best);
-        if (L <= ws) {                                   // read.cpp:217-218
-            const double mean = 100.0 * sum / (double)L;
-            write_read(a, (uint32_t)r, L, mean, mean);
-            continue;
-        }
-        w = sum / (double)ws;                            // read.cpp:223
-        best = w;
-        chain<true, true>(q, ws, lim, ws, t, sum, w, best);
-        if (L <= a.head_len) finish(a, (uint32_t)r, L, sum, best);
-        else { a.it_a[r] = sum; a.it_b[r] = w; a.it_c[r] = best; }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// k_phred_tile: BOTH chains of a read by one warp, one window length (ws bases) per step, exact.
+// Default Phred path: three kernels, all exact, none walks a read base by base in one thread.
+//   k_phred_first  one thread per read: the first window (sum, W0 = fl(sum / ws)) and the sum up to the
+//                  next 16-byte boundary; reads not longer than the window are finished here.
+//   k_phred_sum    one warp per read: the mean's sum, 512 bases per step.
+//   k_phred_win    one warp per read: the window chain's minimum, one window length per step.
 //
 // Lattice identity (as in k_phred_mean_long): while a running double v stays inside one binade
 // [C, 2C) it is a multiple of u = ulp(C), and for 0 <= t < C (IEEE RN, t not exactly half way between
 // two multiples of u)      fl(v + t) = v + r(t),   fl(v - t) = v - r(t),   r(t) = t rounded to the grid u.
-// So the chain is a sum of grid steps, exact in ANY order as long as every partial sum stays inside
-// the binade -- and the rounding r() itself is done by the adder: a lane that walks its bases from an
-// ANCHOR inside the same binade (1.5 C for the window chain, C for the mean's sum) gets exactly the
-// same grid steps as the reference's chain does from its own value.
+// So a chain is a sum of grid steps, exact in ANY order as long as every partial sum stays inside the
+// binade; and inside one binade the BIT PATTERN of a double moves by one unit per grid step, so warp
+// scans and reductions of grid steps are 64-bit integer adds.
 //
-// Layout: step t covers bases [ws + t ws, ws + (t+1) ws); lane l owns K = ceil(ws/32) consecutive
-// bases of it, ALWAYS the same offsets, so the value that leaves the window when lane l adds its
-// k-th base is the value lane l added at its k-th base one step earlier: it is still in a register.
-// Per base: one 16-byte shared-memory gather {q[c], a[c]} (8 lane-private copies, conflict free), one
-// add for the sum, subtract + add + compare for the window.
-//   window: the lane walks x = 0.75 - old_k + new_k ..., keeps its lowest point and its total; one
-//     warp scan of the totals places the lanes (exact: grid multiples), so the absolute running
-//     minimum is min over lanes of (W + prefix + lowest point). The whole read is assumed to keep w
-//     inside [0.5, 1): upper side by construction (every table value is below (1 - 1e-10)/ws, the
-//     first window W0 = fl(sum/ws) is within 1e-13 of the grid sum of its own values, so every later
-//     grid value is below 1 - 4e-10), lower side CHECKED at the end: minimum - max table value >= 0.5
-//     (the lowest point after a subtraction is at most one table value below a point after an
-//     addition). Table values that tie on the grid 2^-53, or lie outside [0, 1), are NaN in the warp's
-//     table: NaN reaches W and the read is rejected. A rejected read goes to k_phred_fallback (the
-//     reference's loop verbatim, one thread).
-//   sum: lane-local acc = C + q + q + ... (C = 2^e, the binade of the running sum s): exact grid steps
-//     while acc < 2C, collected only when the room left in the binade (2C - s, each step adds < 1)
-//     could run out: O(log) warp reductions per binade. The step in which s may cross into the next
-//     binade ("careful" step) is resolved exactly: scan of the lanes' chunk sums, first lane whose
-//     prefix reaches 2C walks its K bases with true adds, the lanes after it redo their chunks on the
-//     coarser grid. Binades in which some table value would tie (host mask; only s < 1024 for the
-//     Phred table) run every step careful with a per-base tie test; a tie, a NaN or anything
-//     unexpected sends that one step to lane 0 and the reference's own loop.
+// k_phred_sum: lane l adds its 16 bases to a lane-local acc that starts at C = 2^e, the binade of the
+//   running sum s: acc = C + q + q + ... rounds every q to the grid of [C, 2C) exactly as s + q would
+//   (the adder does r() for us). The lanes' parts are collected only when the room left in the binade
+//   (2C - s; every base adds at most 1) could run out: O(log) warp reductions per binade. The step in
+//   which s may cross into the next binade ("careful" step) is resolved exactly: integer scan of the
+//   lanes' parts, the first lane whose prefix reaches 2C walks its 16 bases with true adds, the lanes
+//   after it redo their parts on the coarser grid. In a binade in which a table value would tie (host
+//   mask; only s < 1024 for the Phred table, one value each) a step first looks for that byte; a tie,
+//   a NaN (bytes outside the Phred range are NaN in the warp's table) or anything unexpected sends
+//   that one step to lane 0 and the reference's own loop.
+//
+// k_phred_win: step t covers bases [ws + t ws, ws + (t+1) ws); lane l owns K = ceil(ws/32)
+//   consecutive bases of it, ALWAYS the same offsets, so the value that leaves the window when lane l
+//   adds its k-th base is the value lane l added at its k-th base one step earlier: still in a
+//   register. The table holds a[c] already rounded to the grid 2^-53 of [0.5, 1), so per base:
+//   one 8-byte shared-memory gather (16 lane-private copies, conflict free), x += new - old (both
+//   grid multiples: exact), compare. The lane walks from the anchor 0.75; one integer warp scan of the
+//   lanes' totals places them, the absolute running minimum is min over lanes of (W + prefix + lowest
+//   point). The whole read is assumed to keep w inside [0.5, 1): upper side by construction (every
+//   table value is below (1 - 1e-10)/ws, the first window W0 = fl(sum/ws) is within 1e-13 of the grid
+//   sum of its own values, so every later grid value is below 1 - 4e-10), lower side CHECKED at the
+//   end: minimum - 2 max table value >= 0.5 (the point after a subtraction is at most one table value
+//   below a point after an addition). Table values that tie on the grid, or lie outside [0, 1), are
+//   NaN in the warp's table: NaN reaches the walk and the read is rejected. A rejected read goes to
+//   k_phred_fallback (the reference's loop verbatim, one thread).
 // ---------------------------------------------------------------------------------------------
 #define PT_THREADS 256
-#define PT_SMEM (256 * 8 * 16)         // {q, a} x 8 lane-private copies = 32 KiB
+#define PT_SMEM (256 * 16 * 8)         // one table, 16 lane-private copies = 32 KiB
+#define PS_TILE 512
+
+struct TieInfo {
+    unsigned long long any;            // bit e: some table value q ties when added to a sum in [2^e, 2^(e+1))
+    unsigned long long many;           // bit e: more than one does (the step is then walked by lane 0)
+    unsigned char ch[64];              // the one that does, when exactly one
+};
 
 __device__ __forceinline__ int exponent_of(double v) { return (int)((__double2hiint(v) >> 20) & 0x7FF) - 1023; }
 __device__ __forceinline__ double pow2(int e) { return __hiloint2double((e + 1023) << 20, 0); }
-
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ double warp_incl_scan(double v, unsigned lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= (unsigned)d) v += t;
-    }
-    return v;
-}
+
 __device__ __forceinline__ long long warp_incl_scan_ll(long long v, unsigned lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -517,29 +493,205 @@ __device__ __forceinline__ long long warp_incl_scan_ll(long long v, unsigned lan
     }
     return v;
 }
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// table entry of the k-th byte of a chunk: tl + 128 * byte
-__device__ __forceinline__ const double2 *entry_of(const double2 *tl, uint32_t w, int k) {
+// address of table[c] in this lane's copy, c = k-th byte of w
+__device__ __forceinline__ const double *entry_of(const double *tl, uint32_t w, int k) {
     const uint32_t c = __byte_perm(w, 0u, 0x4440u + (unsigned)k);
-    return reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(tl) + (c << 7));
+    return reinterpret_cast<const double *>(reinterpret_cast<const unsigned char *>(tl) + (c << 7));
 }
 
-// the K bytes at byte position pos of a read (any alignment), as ceil(K/4) words
+__global__ void __launch_bounds__(PH_THREADS, 3) k_phred_first(PhredArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Tab t = make_tables(a.lut, smem_raw);
+    const int ws = a.p.window_size;
+    for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (size_t)gridDim.x * blockDim.x) {
+        const int L = a.len[r];
+        const uint8_t *q = a.qual + a.off[r];
+        double sum = 0.0, w = 0.0, best = 0.0;
+        chain<true, false>(q, 0, L < ws ? L : ws, ws, t, sum, w, best);
+        if (L <= ws) {                                   // read.cpp:217-218
+            const double mean = 100.0 * sum / (double)L;
+            write_read(a, (uint32_t)r, L, mean, mean);
+            continue;
+        }
+        a.it_b[r] = sum / (double)ws;                    // read.cpp:223
+        chain<true, false>(q, ws, L < a.head_len ? L : a.head_len, ws, t, sum, w, best);
+        a.it_a[r] = sum;                                 // sum of the first min(L, head_len) bases
+    }
+}
+
+// does this lane's chunk hold the byte that ties in the current binade?
 template <int NW>
-__device__ __forceinline__ void load_chunk(const uint32_t *__restrict__ q32, int pos, int maxword, uint32_t (&o)[NW]) {
+__device__ __forceinline__ bool chunk_has(const uint32_t (&cw)[NW], unsigned ch) {
+    const uint32_t pat = ch * 0x01010101u;
+    uint32_t hit = 0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) hit |= __vcmpeq4(cw[i], pat);
+    return hit != 0u;
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 4) k_phred_sum(PhredArgs a, TieInfo tie) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *tab = reinterpret_cast<double *>(smem_raw);                // q[256][16]
+    __shared__ TieInfo s_tie;
+    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
+    if (threadIdx.x == 0) s_tie = tie;
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        const double q = a.lut[i >> 4];
+        tab[i] = (q >= 0.0 && q < 1.0) ? q : qnan;
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const double *tl = tab + (lane & 15);
+    const int H = a.head_len;
+    const float inv_tile = 1.0f / (float)PS_TILE;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t it = warp; it < a.n; it += n_warps) {
+        const uint32_t r = a.order[it];
+        const int L = a.len[r];
+        if (L <= H) continue;                                          // k_phred_first has the whole sum
+        const uint8_t *q = a.qual + a.off[r];
+        const uint4 *qv = reinterpret_cast<const uint4 *>(q);
+        double s0 = a.it_a[r];
+        long long sb = __double_as_longlong(s0);                       // bit pattern of the collected part of the sum
+        int e = exponent_of(s0);
+        double Cs = pow2(e), acc = Cs;
+        int budget = 0;
+        bool tieflag = e >= 0 && e < 64 && ((s_tie.any >> e) & 1ull);
+        bool nanf = false;
+        uint4 pre = make_uint4(0x21212121u, 0x21212121u, 0x21212121u, 0x21212121u);
+        if (H + 16 * (int)lane < L) pre = __ldg(qv + ((H >> 4) + (int)lane));
+        for (int j = H; j < L; j += PS_TILE) {
+            uint32_t cw[4] = {pre.x, pre.y, pre.z, pre.w};
+            {
+                const int pn = j + PS_TILE + 16 * (int)lane;
+                if (pn < L) pre = __ldg(qv + (pn >> 4));
+            }
+            const int n = (L - j < PS_TILE) ? L - j : PS_TILE;
+            if (n < PS_TILE) {                                         // bytes beyond the read become '!' (q = 0: adds nothing)
+                const int nv = n - 16 * (int)lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int vb = nv - 4 * i;
+                    const uint32_t m = vb >= 4 ? 0xFFFFFFFFu : (vb <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * vb)));
+                    cw[i] = (cw[i] & m) | (0x21212121u & ~m);
+                }
+            }
+            const bool in_range = e >= 5 && e < 52;
+            int mode = 0;                                              // 0: lane-local grid, 1: careful, 2: lane 0 walks the step
+            if (budget == 0 || tieflag) {
+                if (budget == 0) {
+                    nanf |= (acc != acc);
+                    sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));   // grid units, still below 2 Cs
+                    acc = Cs;
+                    if (in_range) {
+                        // every base adds at most 1.0: budget * 512 <= floor(room) - 1 keeps the sum strictly inside the binade
+                        long long room = ((__double_as_longlong(Cs) + (1ll << 52)) - sb) >> (52 - e);
+                        if (room > (1ll << 30)) room = 1ll << 30;
+                        budget = room >= 1 ? (int)((room - 1) >> 9) : 0;
+                    }
+                }
+                if (!in_range || sb <= 0) {
+                    mode = 2;
+                } else {
+                    if (tieflag && (((s_tie.many >> e) & 1ull) || __any_sync(0xffffffffu, chunk_has<4>(cw, s_tie.ch[e])))) mode = 2;
+                    if (mode == 2 && budget > 0) {
+                        sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));
+                        acc = Cs;
+                        budget = 0;
+                    }
+                    if (mode == 0 && budget == 0) mode = 1;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc += *entry_of(tl, cw[k >> 2], k & 3);       // read.cpp:210-211 on the grid of [Cs, 2 Cs)
+            if (mode == 0) {
+                --budget;
+                continue;
+            }
+            // acc = Cs + this lane's part, the collected sum is in sb
+            bool serial = mode == 2 || __any_sync(0xffffffffu, acc != acc);
+            if (!serial) {
+                // the step may cross into the next binade, several times while the sum is still small:
+                // resolve one crossing per round, the lanes after the crossing lane redo their parts on
+                // the coarser grid
+                long long cur = sb;                                    // pattern of the exact sum before lane `lo`
+                int ce = e, lo = 0;
+                double C = Cs, part = acc;
+                for (int round = 0; round < 6; ++round) {
+                    const long long top = __double_as_longlong(C) + (1ll << 52);       // pattern of 2 C
+                    const long long u = (int)lane >= lo ? __double_as_longlong(part) - __double_as_longlong(C) : 0ll;
+                    const long long P = warp_incl_scan_ll(u, lane);
+                    const unsigned cross = __ballot_sync(0xffffffffu, cur + P >= top);
+                    if (cross == 0u) {
+                        sb = cur + __shfl_sync(0xffffffffu, P, 31);
+                        e = ce;
+                        Cs = C;
+                        break;
+                    }
+                    const int lx = __ffs(cross) - 1;
+                    double t = __longlong_as_double(cur + __shfl_sync(0xffffffffu, P - u, lx));   // exact sum before lane lx's part
+                    if ((int)lane == lx) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) t += *entry_of(tl, cw[k >> 2], k & 3);     // true adds (read.cpp:210-211)
+                    }
+                    t = shfl_d(t, lx);
+                    ce += 1;
+                    C = C + C;
+                    bool hit = false;
+                    if ((s_tie.any >> ce) & 1ull) hit = ((s_tie.many >> ce) & 1ull) || __any_sync(0xffffffffu, chunk_has<4>(cw, s_tie.ch[ce]));
+                    if (hit || exponent_of(t) != ce || !(t == t) || round == 5) {
+                        serial = true;
+                        break;
+                    }
+                    cur = __double_as_longlong(t);
+                    lo = lx + 1;
+                    part = C;                                          // the lanes after lx on the coarser grid
+                    if ((int)lane >= lo) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) part += *entry_of(tl, cw[k >> 2], k & 3);
+                    }
+                }
+                if (!serial) tieflag = (s_tie.any >> e) & 1ull;
+            }
+            if (serial) {                                              // the reference's own loop for this step
+                double v = __longlong_as_double(sb);
+                if (lane == 0)
+                    for (int p = 0; p < n; ++p) v += __ldg(a.lut + (unsigned)q[j + p]);
+                v = shfl_d(v, 0);
+                sb = __double_as_longlong(v);
+                e = exponent_of(v);
+                Cs = pow2(e);
+                tieflag = e >= 0 && e < 64 && ((s_tie.any >> e) & 1ull);
+            }
+            acc = Cs;
+            budget = 0;
+        }
+        nanf |= (acc != acc);
+        sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));
+        const bool any_nan = __any_sync(0xffffffffu, nanf);
+        if (lane == 0) a.it_a[r] = any_nan ? qnan : __longlong_as_double(sb);
+    }
+}
+
+// raw words holding the K bytes at byte position pos of a read (any alignment)
+template <int NW>
+__device__ __forceinline__ void load_raw(const uint32_t *__restrict__ q32, int pos, int maxword, uint32_t (&w)[NW + 1]) {
     const int wi = pos >> 2;
-    const unsigned bs = ((unsigned)pos & 3u) * 8u;
-    uint32_t w[NW + 1];
 #pragma unroll
     for (int i = 0; i <= NW; ++i) {
         const int x = wi + i;
         w[i] = __ldg(q32 + (x < maxword ? x : maxword));
     }
+}
+template <int NW>
+__device__ __forceinline__ void align_raw(const uint32_t (&w)[NW + 1], int pos, uint32_t (&o)[NW]) {
+    const unsigned bs = ((unsigned)pos & 3u) * 8u;
 #pragma unroll
     for (int i = 0; i < NW; ++i) o[i] = __funnelshift_r(w[i], w[i + 1], bs);
 }
@@ -548,51 +700,30 @@ __device__ __forceinline__ void load_chunk(const uint32_t *__restrict__ q32, int
 #define PT_ANCHOR_BITS 0x3FE8000000000000ll
 
 // one step of one lane: K bases; TAIL: only the first nvalid bases exist. x ends at anchor + (sum of the
-// lane's grid steps), m is its lowest point after an addition (the anchor itself if the lane owns nothing).
+// lane's grid steps), m is its lowest point (the anchor itself if the lane owns nothing). The window
+// values that leave are the ones this lane added one step earlier (was[]); now[] takes their place.
 template <int K, bool TAIL>
-__device__ __forceinline__ void tile_core(const uint32_t (&cw)[(K + 3) / 4], const double2 *__restrict__ tl, int nvalid,
-                                          double (&old)[K], double &acc, double &x, double &m) {
+__device__ __forceinline__ void win_core(const uint32_t (&cw)[(K + 3) / 4], const double *__restrict__ tl, int nvalid,
+                                         const double (&was)[K], double (&now)[K], double &x, double &m) {
     x = PT_ANCHOR;
     m = PT_ANCHOR;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const double2 e = *entry_of(tl, cw[k >> 2], k & 3);
+        now[k] = *entry_of(tl, cw[k >> 2], k & 3);
         if (!TAIL || k < nvalid) {
-            acc += e.x;                    // read.cpp:210-211 on the grid of the sum's binade
-            x -= old[k];                   // read.cpp:229
-            x += e.y;                      // read.cpp:230
+            x += now[k] - was[k];          // read.cpp:229-230: both are grid multiples, the difference is exact
             m = x < m ? x : m;             // read.cpp:231-232
-            old[k] = e.y;
         }
     }
 }
 
-// chunk sum of one lane on the grid of [C, 2C), optional tie test
 template <int K>
-__device__ __forceinline__ double chunk_sum(const uint32_t (&cw)[(K + 3) / 4], const double2 *__restrict__ tl, int nvalid, double C,
-                                            bool check, bool &bad) {
-    double acc = C;
-    const double half = C * 1.1102230246251565e-16;   // ulp(C) / 2 = C * 2^-53
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        if (k < nvalid) {
-            const double q = entry_of(tl, cw[k >> 2], k & 3)->x;
-            if (check) {
-                const double r = (C + q) - C;
-                bad |= fabs(q - r) == half;           // q - r is exact
-            }
-            acc += q;
-        }
-    }
-    return acc - C;
-}
-
-template <int K>
-__global__ void __launch_bounds__(PT_THREADS, 3) k_phred_tile(PhredArgs a, unsigned long long tie_q) {
+__global__ void __launch_bounds__(PT_THREADS, 4) k_phred_win(PhredArgs a) {
     constexpr int NW = (K + 3) / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *tab = reinterpret_cast<double2 *>(smem_raw);              // [256][8]
+    double *tab = reinterpret_cast<double *>(smem_raw);                // a[256][16] on the grid 2^-53
     __shared__ double s_amax;
+    __shared__ uint32_t s_mask[32][4];
     const int ws = a.p.window_size;
     const double qnan = __longlong_as_double(0x7FF8000000000000ll);
     if (threadIdx.x == 0) {
@@ -601,151 +732,97 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_phred_tile(PhredArgs a, unsig
             const double v = a.lut[256 + c];
             if (v >= 0.0 && v > mx && v * (double)ws <= 1.0 - 1e-10) mx = v;
         }
-        s_amax = mx;
+        s_amax = (0.5 + mx) - 0.5;                                     // on the grid
     }
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-        const int c = i >> 3;
-        double q = a.lut[c], v = a.lut[256 + c];
-        if (!(q >= 0.0 && q < 1.0)) q = qnan;
+    if (threadIdx.x < 32) {
+        // bytes beyond the lane's share read as '!' (a = 0: no effect on the chain)
+        const int nb = max(0, min(K, ws - K * (int)threadIdx.x));
+        for (int i = 0; i < 2; ++i) {
+            uint32_t m = 0;
+            for (int b = 0; b < 4; ++b)
+                if (4 * i + b < nb) m |= 0xFFu << (8 * b);
+            s_mask[threadIdx.x][i] = m;
+            s_mask[threadIdx.x][2 + i] = 0x21212121u & ~m;
+        }
+    }
+    for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+        double v = a.lut[256 + (i >> 4)];
         bool ok = v >= 0.0 && v * (double)ws <= 1.0 - 1e-10;
         if (ok && v > 0.0) {
             const double sc = ldexp(v, 53);                           // exact; v < 1 so sc < 2^53
             ok = (sc - floor(sc)) != 0.5;                              // would tie on the grid of [0.5, 1)
         }
-        if (!ok) v = qnan;
-        tab[i] = make_double2(q, v);
+        tab[i] = ok ? (0.5 + v) - 0.5 : qnan;                          // a[c] rounded to the grid 2^-53 of [0.5, 1)
     }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31;
-    const double2 *tl = tab + (lane & 7);
-    const double thr = 0.5 + s_amax;
-    const double wsd = (double)ws;
-    const int nb_lane = max(0, min(K, ws - K * (int)lane));          // bases of a full step owned by this lane
-    // bytes beyond the lane's share read as '!' (q = a = 0: no effect on either chain)
+    const double *tl = tab + (lane & 15);
+    const double thr = 0.5 + 2.0 * s_amax;
+    const int nb_lane = max(0, min(K, ws - K * (int)lane));           // bases of a full step owned by this lane
+    const int lpos = K * (int)lane;
     uint32_t keep[NW], fill[NW];
 #pragma unroll
     for (int i = 0; i < NW; ++i) {
-        uint32_t m = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (4 * i + b < nb_lane) m |= 0xFFu << (8 * b);
-        keep[i] = m;
-        fill[i] = 0x21212121u & ~m;
+        keep[i] = s_mask[lane][i];
+        fill[i] = s_mask[lane][2 + i];
     }
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t it = warp; it < a.n; it += n_warps) {
         const uint32_t r = a.order[it];
         const int L = a.len[r];
-        if (L <= ws) continue;                                         // finished by k_phred_head
-        const uint8_t *q = a.qual + a.off[r];
-        const uint32_t *q32 = reinterpret_cast<const uint32_t *>(q);
+        if (L <= ws) continue;                                         // finished by k_phred_first
+        const uint32_t *q32 = reinterpret_cast<const uint32_t *>(a.qual + a.off[r]);
         const int maxword = (((L + 63) & ~63) >> 2) - 1;
-        double s = a.it_a[r];                                          // sum of the first window (k_phred_head)
-        const double W0 = a.it_b[r];                                   // fl(sum / ws), read.cpp:223
+        const double W0 = a.it_b[r];                                   // fl(sum of the first window / ws), read.cpp:223
         bool reject = !(W0 >= thr && W0 < 1.0);
         // the window chain as bit patterns: inside [0.5, 1) one grid step is one unit of the pattern
         long long Wb = __double_as_longlong(W0), mnb = Wb;
         bool nanf = false;
-        double old[K];
-        {
-            uint32_t cw[NW];
-            load_chunk<NW>(q32, K * (int)lane, maxword, cw);
+        if (!reject) {
+            double va[K], vb[K];
+            {
+                uint32_t raw[NW + 1], cw[NW];
+                load_raw<NW>(q32, lpos, maxword, raw);
+                align_raw<NW>(raw, lpos, cw);
 #pragma unroll
-            for (int k = 0; k < K; ++k) old[k] = (k < nb_lane) ? entry_of(tl, cw[k >> 2], k & 3)->y : 0.0;
+                for (int k = 0; k < K; ++k) va[k] = (k < nb_lane) ? *entry_of(tl, cw[k >> 2], k & 3) : 0.0;
+            }
+            uint32_t pre[NW + 1];
+            load_raw<NW>(q32, ws + lpos, maxword, pre);
+            int j = ws;
+            // one step: bases [j, j + ws) (fewer in the last one)
+#define PT_STEP(WAS, NOW)                                                                                     \
+            {                                                                                                 \
+                uint32_t cw[NW];                                                                              \
+                align_raw<NW>(pre, j + lpos, cw);                                                             \
+                if (j + ws < L) load_raw<NW>(q32, j + ws + lpos, maxword, pre);                               \
+                const int n = L - j;                                                                          \
+                double x, m;                                                                                  \
+                if (n >= ws) {                                                                                \
+                    _Pragma("unroll") for (int i = 0; i < NW; ++i) cw[i] = (cw[i] & keep[i]) | fill[i];       \
+                    win_core<K, false>(cw, tl, K, WAS, NOW, x, m);                                            \
+                } else {                                                                                      \
+                    win_core<K, true>(cw, tl, max(0, min(nb_lane, n - lpos)), WAS, NOW, x, m);                \
+                }                                                                                             \
+                nanf |= (x != x);                                                                             \
+                const long long nx = __double_as_longlong(x) - PT_ANCHOR_BITS;                                \
+                const long long inc = warp_incl_scan_ll(nx, lane);                                            \
+                const long long cand = Wb + (inc - nx) + (__double_as_longlong(m) - PT_ANCHOR_BITS);          \
+                mnb = cand < mnb ? cand : mnb;                                                                \
+                Wb += __shfl_sync(0xffffffffu, inc, 31);                                                      \
+                j += ws;                                                                                      \
+            }
+            while (true) {
+                PT_STEP(va, vb)
+                if (j >= L) break;
+                PT_STEP(vb, va)
+                if (j >= L) break;
+            }
+#undef PT_STEP
         }
-        int e = exponent_of(s);
-        double Cs = pow2(e);
-        double acc = Cs;
-        int budget = 0;                                                // steps the sum may still take on the lane-local grid
-        uint32_t pre[NW];
-        if (!reject) load_chunk<NW>(q32, ws + K * (int)lane, maxword, pre);
-        for (int j = ws; j < L && !reject; j += ws) {
-            uint32_t cw[NW];
-#pragma unroll
-            for (int i = 0; i < NW; ++i) cw[i] = pre[i];
-            if (j + ws < L) load_chunk<NW>(q32, j + ws + K * (int)lane, maxword, pre);
-            const int n = (L - j < ws) ? L - j : ws;
-            // ---- mean: may this step run on the lane-local grid? ----
-            if (budget == 0) {
-                s += warp_sum(acc - Cs);                               // exact, still below 2 Cs
-                acc = Cs;
-                if (e >= 5 && e < 62 && !((tie_q >> e) & 1ull)) {
-                    const double room = (Cs + Cs) - s;                 // every base adds at most 1
-                    budget = __double2int_rd(fmin(room / wsd, 1.0e6)) - 1;
-                    if (budget < 0) budget = 0;
-                }
-            }
-            const bool fast = budget > 0;
-            double x, m;
-            int nvalid = nb_lane;
-            if (n == ws) {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) cw[i] = (cw[i] & keep[i]) | fill[i];
-                tile_core<K, false>(cw, tl, K, old, acc, x, m);
-            } else {
-                nvalid = max(0, min(nb_lane, n - K * (int)lane));
-                tile_core<K, true>(cw, tl, nvalid, old, acc, x, m);
-            }
-            // ---- window: place the lanes (integer scan of the grid steps) ----
-            nanf |= (x != x);
-            const long long nx = __double_as_longlong(x) - PT_ANCHOR_BITS;
-            const long long inc = warp_incl_scan_ll(nx, lane);
-            const long long cand = Wb + (inc - nx) + (__double_as_longlong(m) - PT_ANCHOR_BITS);   // lowest point of this lane
-            mnb = cand < mnb ? cand : mnb;
-            Wb += __shfl_sync(0xffffffffu, inc, 31);
-            // ---- mean ----
-            if (fast) {
-                --budget;
-            } else {
-                bool ser = !(e >= 5 && e < 62) || !(s > 0.0);
-                if (!ser) {
-                    bool bad = false;
-                    const double cs = chunk_sum<K>(cw, tl, nvalid, Cs, (tie_q >> e) & 1ull, bad);
-                    const double P = warp_incl_scan(cs, lane);
-                    const double Pall = shfl_d(P, 31);
-                    if (__any_sync(0xffffffffu, bad) || !(Pall == Pall)) {
-                        ser = true;
-                    } else {
-                        const unsigned cross = __ballot_sync(0xffffffffu, s + P >= Cs + Cs);
-                        if (cross == 0u) {
-                            s += Pall;
-                        } else {
-                            const int lx = __ffs(cross) - 1;
-                            double t = s + shfl_d(P - cs, lx);         // exact sum before lane lx's chunk
-                            if ((int)lane == lx) {
-#pragma unroll
-                                for (int k = 0; k < K; ++k)
-                                    if (k < nvalid) t += entry_of(tl, cw[k >> 2], k & 3)->x;   // true adds (read.cpp:210-211)
-                            }
-                            t = shfl_d(t, lx);
-                            const double C2 = Cs + Cs;
-                            bool bad2 = false;
-                            const double cs2 = chunk_sum<K>(cw, tl, (int)lane > lx ? nvalid : 0, C2, (tie_q >> (e + 1)) & 1ull, bad2);
-                            const double rest = warp_sum(cs2);
-                            if (exponent_of(t) != e + 1 || __any_sync(0xffffffffu, bad2) || !(t + rest < C2 + C2)) {
-                                ser = true;
-                            } else {
-                                s = t + rest;
-                                e += 1;
-                                Cs = C2;
-                            }
-                        }
-                    }
-                }
-                if (ser) {                                             // the reference's own loop for this step
-                    if (lane == 0)
-                        for (int p = 0; p < n; ++p) s += __ldg(a.lut + (unsigned)q[j + p]);
-                    s = shfl_d(s, 0);
-                    e = exponent_of(s);
-                    Cs = pow2(e);
-                }
-                acc = Cs;
-                budget = 0;
-            }
-        }
+        const double s = a.it_a[r];                                    // the mean's sum (k_phred_first / k_phred_sum)
         double mn = 0.0;
         if (!reject) {
-            s += warp_sum(acc - Cs);
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 const long long t = __shfl_xor_sync(0xffffffffu, mnb, o);
@@ -772,12 +849,18 @@ static int ensure_lut(fl_ctx *ctx) {
     // binades [2^e, 2^(e+1)) of the running sum in which some table value in [0,1) would sit exactly
     // on a rounding tie (its bits below 2^(e-52) are 100..0): only there k_phred_mean_long tests ties
     ctx->tie_binades = 0;
+    ctx->tie_many = 0;
+    memset(ctx->tie_char, 0, sizeof(ctx->tie_char));
     for (int e = 0; e < 64; ++e)
         for (int c = 0; c < 256; ++c) {
             const double q = h[c];
             if (!(q > 0.0 && q < 1.0)) continue;
             const double scaled = ldexp(q, 52 - e);          // exact
-            if (scaled - floor(scaled) == 0.5) ctx->tie_binades |= 1ull << e;
+            if (scaled - floor(scaled) == 0.5) {
+                if (ctx->tie_binades & (1ull << e)) ctx->tie_many |= 1ull << e;
+                ctx->tie_binades |= 1ull << e;
+                ctx->tie_char[e] = (unsigned char)c;
+            }
         }
     // same for the window table a[] and the binades [2^-e, 2^(1-e)) of w (bit e), (kept for diagnostics)
     ctx->tie_binades_a = 0;
@@ -805,7 +888,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
     const int ws = ctx->p.window_size;
     if (ctx->phred_mode == 1 && ws >= 16 && ws <= 256) {
-        // default: one warp per read, both chains by exact grid arithmetic (k_phred_tile)
+        // default: one warp per read, both chains by exact grid arithmetic (k_phred_sum, k_phred_win)
         FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
         FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
         PhredArgs a{};
@@ -820,7 +903,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
         a.read_base = rb; a.row_base = wb;
         a.order = ctx->sc_order.p;
-        a.head_len = ws;                                  // k_phred_head: the first window, and reads not longer than it
+        a.head_len = (ws + 15) & ~15;                     // k_phred_first sums up to here; k_phred_sum takes over (16-byte loads)
         FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n + 8, 0, st));
         a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n; a.it_c = ctx->sc_f64.p + 2 * n;
         FL_CUDA(ctx, ctx->sc_u32a.reserve(n + 2, 0, st));
@@ -828,30 +911,38 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         FL_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, sizeof(uint32_t), st));
         static bool tile_attr_set = false;
         if (!tile_attr_set) {
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_head, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_first, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             tile_attr_set = true;
         }
         {
             unsigned hb = fl_blocks(n, PH_THREADS);
             if (hb > (unsigned)ctx->sm_count * 3) hb = (unsigned)ctx->sm_count * 3;
-            k_phred_head<<<hb, PH_THREADS, PH_SMEM, st>>>(a);
+            k_phred_first<<<hb, PH_THREADS, PH_SMEM, st>>>(a);
             ctx->launches++;
         }
         unsigned blocks = fl_blocks(n * 32, PT_THREADS);
-        const unsigned cap = (unsigned)ctx->sm_count * 4;
+        const int occ = ctx->phred_occupancy >= 1 && ctx->phred_occupancy <= 6 ? ctx->phred_occupancy : 4;
+        const unsigned cap = (unsigned)ctx->sm_count * (unsigned)occ;
         if (blocks > cap) blocks = cap;
         {
+            // timed as one scoring pass: the sum kernel and the window kernel
             KernelTimer kt(ctx, FL_KERNEL_SCORE_PHRED);
-            if (ws <= 64) k_phred_tile<2><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
-            else if (ws <= 128) k_phred_tile<4><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
-            else k_phred_tile<8><<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ctx->tie_binades);
+            TieInfo ti;
+            ti.any = ctx->tie_binades;
+            ti.many = ctx->tie_many;
+            memcpy(ti.ch, ctx->tie_char, 64);
+            k_phred_sum<<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ti);
+            if (ws <= 64) k_phred_win<2><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
+            else if (ws <= 128) k_phred_win<4><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
+            else k_phred_win<8><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
         }
-        ctx->launches++;
-        k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);   // reads the warp kernel rejected (normally none)
+        ctx->launches += 2;
+        k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);   // reads the window kernel rejected (normally none)
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
         ctx->n_reads += n;
