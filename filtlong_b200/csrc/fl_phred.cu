@@ -65,6 +65,7 @@ struct PhredArgs {
     unsigned long long n_items;
     double *it_a, *it_b, *it_c;             // per item: MEAN: sum | SEG: entry, exit, best
     uint32_t *fallback;                     // [0] = count, [1..] = reads to re-score serially
+    unsigned long long *work;               // [0], [1]: next read (in `order`) for k_phred_sum / k_phred_win
     int head_len;                           // k_phred_first: bases whose sum the per-read first pass takes
 };
 
@@ -550,8 +551,12 @@ __global__ void __launch_bounds__(PT_THREADS, 4) k_phred_sum(PhredArgs a, TieInf
     const double *tl = tab + (lane & 15);
     const int H = a.head_len;
     const float inv_tile = 1.0f / (float)PS_TILE;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t it = warp; it < a.n; it += n_warps) {
+    // reads are taken longest first from a shared counter: the warps finish together
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(a.work + 0, 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= a.n) break;
         const uint32_t r = a.order[it];
         const int L = a.len[r];
         if (L <= H) continue;                                          // k_phred_first has the whole sum
@@ -766,8 +771,11 @@ __global__ void __launch_bounds__(PT_THREADS, 4) k_phred_win(PhredArgs a) {
         keep[i] = s_mask[lane][i];
         fill[i] = s_mask[lane][2 + i];
     }
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t it = warp; it < a.n; it += n_warps) {
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(a.work + 1, 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= a.n) break;
         const uint32_t r = a.order[it];
         const int L = a.len[r];
         if (L <= ws) continue;                                         // finished by k_phred_first
@@ -909,6 +917,8 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         FL_CUDA(ctx, ctx->sc_u32a.reserve(n + 2, 0, st));
         a.fallback = ctx->sc_u32a.p;
         FL_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, sizeof(uint32_t), st));
+        a.work = ctx->d_scalars + 24;
+        FL_CUDA(ctx, cudaMemsetAsync(a.work, 0, 2 * sizeof(unsigned long long), st));
         static bool tile_attr_set = false;
         if (!tile_attr_set) {
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
