@@ -4,12 +4,17 @@
 //     sum += q[c_j]                                   (read.cpp:208-213)
 //     w -= a[c_{j-ws}];  w += a[c_j];  min = min(min, w)   (read.cpp:226-232)
 // with q[c] = 1 - 10^(-(c-33)/10) and a[c] = q[c] / window_size. Their low-order bits depend on that
-// order, and hard thresholds (--min_mean_q / --min_window_q) compare them, so we reproduce the
-// order exactly: every chain is walked by ONE thread with IEEE double adds (file built with
-// --fmad=false), q[] / a[] come from 256-entry tables evaluated with the host libm and replicated
-// in shared memory so that each lane owns its banks (conflict-free 16-byte / 8-byte gathers).
+// order, and hard thresholds (--min_mean_q / --min_window_q) compare them, so every path in this file
+// returns the reference's bits (file built with --fmad=false, q[] / a[] are 256-entry tables evaluated
+// with the host libm and replicated in shared memory so that each lane owns its banks).
 //
-// Work decomposition (what makes this a GPU algorithm rather than 2 M independent CPU loops):
+// Two implementations:
+//   * DEFAULT (window sizes 16..256): k_phred_first + k_phred_sum + k_phred_win, one warp per read,
+//     exact lattice arithmetic inside binades -- see the comment block above k_phred_first.
+//   * Work items (FL_PHRED_MODE=0, and every other window size), described next. Also the home of
+//     k_phred_fallback, the reference's loop verbatim, which re-scores whatever a fast path rejects.
+//
+// Work-item decomposition:
 //   * reads up to PH_LONG bases: one work item, the fused loop (sum and window together);
 //   * longer reads: one item for the mean chain plus one item per PH_SEG-base SEGMENT of the window
 //     chain. A segment needs the exact value of w at its first base. It is obtained WITHOUT running
@@ -20,9 +25,7 @@
 //     sequential recurrence from its predicted entry, and k_phred_merge accepts a read only if each
 //     segment's exit value equals the next segment's predicted entry bit-for-bit (induction from
 //     the exact first window). A read that fails the check (binade crossing, round-to-even tie) is
-//     re-scored by the plain fused loop. Results are therefore always the reference's bits; the
-//     prediction only buys parallelism (a 1 Mbp read is 60 concurrent segments instead of a 1 M
-//     step serial tail);
+//     re-scored by the plain fused loop;
 //   * items are issued in descending cost order over a persistent grid.
 #include "fl_device.cuh"
 
