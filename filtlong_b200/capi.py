@@ -100,6 +100,7 @@ class SynthReads(C.Structure):
 _P = C.c_void_p
 SYMBOLS = [
     ("fl_ctx_create", C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(_P)]),
+    ("fl_device_warmup", C.c_int, [C.c_int]),
     ("fl_ctx_destroy", None, [_P]),
     ("fl_last_error", C.c_char_p, [_P]),
     ("fl_ctx_set_stream", C.c_int, [_P, _P]),

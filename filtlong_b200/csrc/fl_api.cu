@@ -26,6 +26,11 @@ static int validate_params(const fl_params *p, std::string &why) {
     return FL_OK;
 }
 
+extern "C" int fl_device_warmup(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) return FL_ENODEV;
+    return cudaFree(nullptr) == cudaSuccess ? FL_OK : FL_ENODEV;
+}
+
 extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) {
     if (!out) return FL_EINVAL;
     *out = nullptr;
@@ -173,19 +178,42 @@ extern "C" void fl_pack_sequence(const char *seq, const char *qual, int64_t len,
                                  uint8_t *qual_out, uint32_t *nmask) {
     if (qual_out && qual) memcpy(qual_out + off, qual, (size_t)len);
     if (!seq2b && !nmask) return;
-    for (int64_t i = 0; i < len; ++i) {
-        uint32_t code = 0, other = 0;
-        switch (seq[i]) {                         // kmers.cpp:176-196
-            case 'A': case 'a': code = 0; break;
-            case 'C': case 'c': code = 1; break;
-            case 'G': case 'g': code = 2; break;
-            case 'T': case 't': code = 3; break;
-            default: other = 1; break;
+    // kmers.cpp:176-196: A/a 0, C/c 1, G/g 2, T/t 3, anything else 0 (and flagged in nmask)
+    static const struct Tab {
+        uint8_t code[256], other[256];
+        Tab() {
+            for (int i = 0; i < 256; ++i) { code[i] = 0; other[i] = 1; }
+            const char *acgt = "AaCcGgTt";
+            for (int i = 0; i < 8; ++i) { code[(unsigned char)acgt[i]] = (uint8_t)(i >> 1); other[(unsigned char)acgt[i]] = 0; }
         }
+    } tab;
+    const unsigned char *s = reinterpret_cast<const unsigned char *>(seq);
+    int64_t i = 0;
+    // head up to the next 32-base boundary of the arena, then whole 32-base groups, then the tail
+    auto slow = [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const uint64_t b = off + (uint64_t)k;
+            const uint32_t code = tab.code[s[k]];
+            if (seq2b && code) seq2b[b >> 4] |= code << (30 - 2 * (b & 15));
+            if (nmask && tab.other[s[k]]) nmask[b >> 5] |= 1u << (b & 31);
+        }
+    };
+    const int64_t head = (int64_t)((32 - (off & 31)) & 31);
+    slow(0, head < len ? head : len);
+    i = head < len ? head : len;
+    for (; i + 32 <= len; i += 32) {
         const uint64_t b = off + (uint64_t)i;
-        if (seq2b && code) seq2b[b >> 4] |= code << (30 - 2 * (b & 15));
-        if (nmask && other) nmask[b >> 5] |= 1u << (b & 31);
+        uint32_t w0 = 0, w1 = 0, m = 0;
+        for (int k = 0; k < 16; ++k) {
+            w0 = (w0 << 2) | tab.code[s[i + k]];
+            w1 = (w1 << 2) | tab.code[s[i + 16 + k]];
+            m |= (uint32_t)tab.other[s[i + k]] << k;
+            m |= (uint32_t)tab.other[s[i + 16 + k]] << (16 + k);
+        }
+        if (seq2b) { seq2b[b >> 4] |= w0; seq2b[(b >> 4) + 1] |= w1; }
+        if (nmask && m) nmask[b >> 5] |= m;
     }
+    slow(i, len);
 }
 
 extern "C" void fl_phred_luts(int32_t window_size, double *q256, double *a256) {

@@ -15,6 +15,14 @@ void HostArena::add(const char *seq, const char *qual, int64_t len) {
                      want_qual_ && qual ? qual_.data() : nullptr, want_nmask_ ? nmask_.data() : nullptr);
 }
 
+void HostArena::reserve(uint64_t padded_bases, uint32_t sequences) {
+    off_.reserve(sequences);
+    len_.reserve(sequences);
+    if (want_seq_) seq2b_.reserve((size_t)(padded_bases >> 4));
+    if (want_nmask_) nmask_.reserve((size_t)(padded_bases >> 5));
+    if (want_qual_) qual_.reserve((size_t)padded_bases);
+}
+
 void HostArena::clear() {
     off_.clear();
     len_.clear();

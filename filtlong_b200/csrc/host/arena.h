@@ -14,6 +14,7 @@ public:
     HostArena(bool want_seq, bool want_qual, bool want_nmask) : want_seq_(want_seq), want_qual_(want_qual), want_nmask_(want_nmask) {}
     void add(const char *seq, const char *qual, int64_t len);
     void clear();
+    void reserve(uint64_t padded_bases, uint32_t sequences);   // capacity hint: no reallocation while a batch grows
     bool empty() const { return off_.empty(); }
     uint32_t count() const { return (uint32_t)off_.size(); }
     uint64_t bases() const { return bases_; }

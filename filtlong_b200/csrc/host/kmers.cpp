@@ -15,17 +15,25 @@ void Kmers::check(fl_ctx *ctx, int rc, const char *what) {
 
 Kmers::Kmers() : Kmers(0) {}
 
-Kmers::Kmers(int device) {
-    fl_params p{};
-    p.window_size = 250;
-    p.length_weight = p.mean_q_weight = p.window_q_weight = 1.0;
-    int rc = fl_ctx_create(&p, device, &ctx_);
-    if (rc != FL_OK) throw std::runtime_error(std::string("fl_ctx_create: ") + fl_last_error(nullptr));
+Kmers::Kmers(int device) : device_(device) {}
+
+fl_ctx *Kmers::context() {
+    if (!ctx_) {
+        fl_params p{};
+        p.window_size = 250;
+        p.length_weight = p.mean_q_weight = p.window_q_weight = 1.0;
+        int rc = fl_ctx_create(&p, device_, &ctx_);
+        if (rc != FL_OK) throw std::runtime_error(std::string("fl_ctx_create: ") + fl_last_error(nullptr));
+    }
+    return ctx_;
 }
 
-Kmers::~Kmers() { fl_ctx_destroy(ctx_); }
+Kmers::~Kmers() {
+    if (ctx_) fl_ctx_destroy(ctx_);
+}
 
 uint64_t Kmers::size() {
+    if (!ctx_) return 0;                                               // nothing was ever added
     uint64_t n = 0;
     check(ctx_, fl_kmers_finalize(ctx_, &n), "fl_kmers_finalize");
     return n;
@@ -55,7 +63,8 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
     auto flush = [&]() {
         if (arena.empty()) return;
         fl_batch b = arena.batch();
-        check(ctx_, fl_kmers_add_batch(ctx_, &b, multi ? 1 : 0), "fl_kmers_add_batch");
+        fl_ctx *c = context();
+        check(c, fl_kmers_add_batch(c, &b, multi ? 1 : 0), "fl_kmers_add_batch");
         arena.clear();
         print_hash_progress(filename, base_count);
     };
@@ -74,6 +83,7 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
 
 bool Kmers::is_kmer_present(uint32_t kmer) {
     uint8_t out = 0;
+    if (!ctx_) return false;
     check(ctx_, fl_kmers_contains(ctx_, &kmer, 1, &out), "fl_kmers_contains");
     return out != 0;
 }

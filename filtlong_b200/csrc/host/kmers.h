@@ -10,13 +10,15 @@
 
 class Kmers {
 public:
-    Kmers();                       // throws std::runtime_error if no CUDA device is usable (no CPU fallback)
+    // The CUDA context is created on first use (the first reference file, the first batch of
+    // reads, ...): that call throws std::runtime_error if no CUDA device is usable (no CPU fallback).
+    Kmers();
     explicit Kmers(int device);
     ~Kmers();
     Kmers(const Kmers &) = delete;
     Kmers &operator=(const Kmers &) = delete;
 
-    bool empty() { return size() == 0; }                               // kmers.h:34
+    bool empty() { return !ctx_ || size() == 0; }                      // kmers.h:34
     void add_read_fastqs(std::vector<std::string> filenames);          // kmers.h:36
     void add_assembly_fasta(std::string filename);                     // kmers.h:37
     bool is_kmer_present(uint32_t kmer);                               // kmers.h:38
@@ -28,10 +30,11 @@ public:
 
     // additions of the B200 build
     uint64_t size();               // m_kmers.size()
-    fl_ctx *context() { return ctx_; }
+    fl_ctx *context();
     static void check(fl_ctx *ctx, int rc, const char *what);          // throws on a non-zero status
 
 private:
     int add_reference(const std::string &filename, bool require_multiple_copies);   // kmers.cpp:75-134
     fl_ctx *ctx_ = nullptr;
+    int device_ = 0;
 };

@@ -7,11 +7,14 @@
 // the input and prints the survivors exactly like main.cpp:263-313.
 #include <zlib.h>
 
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -23,6 +26,30 @@
 
 #define PROGRAM_VERSION "0.3.1"
 
+// FL_CLI_TIMING=1: wall-clock seconds per phase on stderr after the run (never on by default: the
+// stderr log is part of the drop-in surface)
+namespace {
+struct PhaseTimer {
+    bool on = getenv("FL_CLI_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    std::string report;
+    void mark(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[128];
+        snprintf(buf, sizeof buf, "[timing] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - last).count());
+        report += buf;
+        last = now;
+    }
+    ~PhaseTimer() {
+        if (!on) return;
+        char buf[128];
+        snprintf(buf, sizeof buf, "[timing] %-28s %8.3f s\n", "total", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        fputs((report + buf).c_str(), stderr);
+    }
+};
+}  // namespace
+
 int main(int argc, char **argv) {
     Arguments args(argc, argv);
     if (args.parsing_result == BAD) return 1;
@@ -33,11 +60,20 @@ int main(int argc, char **argv) {
     }
     std::ios::sync_with_stdio(false);
     std::cerr << "\n";
+    PhaseTimer timer;
+    // The CUDA driver and context take about a second to come up on a B200: start that now, on
+    // its own thread, and parse / pack the first records meanwhile (Kmers creates its context on
+    // first use). Joined on every way out of main.
+    struct Warmup {
+        std::thread t{[] { (void)fl_device_warmup(0); }};
+        ~Warmup() { if (t.joinable()) t.join(); }
+    } warmup;
     try {
         Kmers kmers;                                                      // main.cpp:53-59
         if (args.assembly_set) kmers.add_assembly_fasta(args.assembly);
         if (!args.short_reads.empty()) kmers.add_read_fastqs(args.short_reads);
         const bool kmers_empty = kmers.empty();
+        timer.mark("reference k-mers (+ CUDA init)");
 
         // ---- pass 1: parse, pack and score (main.cpp:61-130) ----
         long long total_bases = 0, last_progress = 0;
@@ -46,6 +82,7 @@ int main(int argc, char **argv) {
         std::unordered_set<std::string> seen_names;
         bool any_fasta = false, any_fastq = false;
         const unsigned long long kBatchBases = 512ull << 20;
+        reads.reserve(kBatchBases + (4ull << 20), 1u << 18);
         unsigned long long queued = 0;
         size_t verbose_done = 0;
         auto verbose_flush = [&]() {
@@ -106,6 +143,7 @@ int main(int argc, char **argv) {
             }
         }
         reads.flush();
+        timer.mark("pass 1 (parse, pack, push)");
         verbose_flush();
         if (!args.verbose) print_read_score_progress((long long)reads.n_reads(), total_bases);
         std::cerr << "\n";
@@ -113,6 +151,7 @@ int main(int argc, char **argv) {
 
         // ---- normalise, final score, target (main.cpp:136-261), on the GPU ----
         fl_summary summary = reads.finalize(total_bases);
+        timer.mark("finalize + download");
         size_t longest_read_name = 0;
         if (args.verbose)
             for (size_t row = 0; row < reads.n_rows(); ++row) longest_read_name = std::max(longest_read_name, reads.row_name(row).size());
@@ -183,6 +222,7 @@ int main(int argc, char **argv) {
             fwrite(out.data(), 1, out.size(), stdout);
             fflush(stdout);
         }
+        timer.mark("pass 2 (parse, print)");
         std::cerr << "\n";
     } catch (const std::exception &e) {
         std::cerr << "\nError: " << e.what() << "\n";

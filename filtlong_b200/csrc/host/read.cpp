@@ -26,10 +26,20 @@ fl_params params_from_arguments(const Arguments &a) {
 // ReadSet
 // ---------------------------------------------------------------------------------------------
 ReadSet::ReadSet(Kmers *kmers, Arguments *args) : kmers_(kmers), args_(args) {
-    fl_params p = params_from_arguments(*args);
-    Kmers::check(kmers->context(), fl_ctx_set_params(kmers->context(), &p), "fl_ctx_set_params");
+    // nothing here touches the GPU: records can be parsed and packed while the CUDA context is still
+    // coming up (Kmers creates it on first use); the parameters are set with the first batch
     kmer_mode_ = !kmers->empty();                          // read.cpp:35
     arena_ = new HostArena(kmer_mode_, !kmer_mode_, false);
+}
+
+fl_ctx *ReadSet::ready_context() {
+    fl_ctx *c = kmers_->context();
+    if (!params_set_) {
+        fl_params p = params_from_arguments(*args_);
+        Kmers::check(c, fl_ctx_set_params(c, &p), "fl_ctx_set_params");
+        params_set_ = true;
+    }
+    return c;
 }
 
 ReadSet::~ReadSet() { delete arena_; }
@@ -41,16 +51,19 @@ void ReadSet::add(const std::string &name, const char *seq, const char *qscores,
     arena_->add(seq, qscores, length);
 }
 
+void ReadSet::reserve(uint64_t bases, uint32_t reads) { arena_->reserve(bases + 64ull * reads, reads); }
+
 void ReadSet::flush() {
     if (arena_->empty()) return;
     fl_batch b = arena_->batch();
-    Kmers::check(kmers_->context(), fl_reads_push(kmers_->context(), &b), "fl_reads_push");
+    fl_ctx *c = ready_context();
+    Kmers::check(c, fl_reads_push(c, &b), "fl_reads_push");
     arena_->clear();
 }
 
 void ReadSet::download() {
     flush();
-    fl_ctx *c = kmers_->context();
+    fl_ctx *c = ready_context();
     uint64_t nr = 0, nw = 0;
     Kmers::check(c, fl_reads_count(c, &nr, &nw, nullptr), "fl_reads_count");
     length.resize(nr); first.resize(nr); last.resize(nr); n_bad.resize(nr); n_child.resize(nr);
@@ -76,7 +89,8 @@ void ReadSet::download() {
 fl_summary ReadSet::finalize(long long total_bases) {
     flush();
     fl_summary s{};
-    Kmers::check(kmers_->context(), fl_finalize(kmers_->context(), total_bases, &s), "fl_finalize");
+    fl_ctx *c = ready_context();
+    Kmers::check(c, fl_finalize(c, total_bases, &s), "fl_finalize");
     download();
     return s;
 }

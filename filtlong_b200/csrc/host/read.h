@@ -58,6 +58,7 @@ public:
     ReadSet &operator=(const ReadSet &) = delete;
     // queues one record (buffers are copied / packed inside the call, like read.cpp does with kseq's)
     void add(const std::string &name, const char *seq, const char *qscores, int length);
+    void reserve(uint64_t bases, uint32_t reads);  // capacity hint for one batch
     void flush();                                  // scores what is queued (fl_reads_push)
     void download();                               // per-read and per-row result arrays -> host
     fl_summary finalize(long long total_bases);    // main.cpp:169-261 on the GPU, then download()
@@ -81,9 +82,11 @@ public:
     std::vector<uint8_t> row_passed, row_pfinal;
 
 private:
+    fl_ctx *ready_context();                       // the context, with this run's parameters set
     Kmers *kmers_;
     Arguments *args_;
     class HostArena *arena_;
     bool kmer_mode_;
+    bool params_set_ = false;
     friend class Read;
 };

@@ -79,6 +79,11 @@ typedef struct fl_ctx fl_ctx;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int fl_ctx_create(const fl_params *params, int device, fl_ctx **out);
+/* Optional: initialise the CUDA driver and the device's primary context (0.5-1.5 s on a B200) from
+ * any thread, e.g. while the caller is still parsing its input (the reference has no counterpart:
+ * its Kmers / Read constructors are ready instantly, src/main.cpp:53,108). fl_ctx_create works
+ * without it. Returns FL_OK or FL_ENODEV. */
+int fl_device_warmup(int device);
 void fl_ctx_destroy(fl_ctx *ctx);
 const char *fl_last_error(const fl_ctx *ctx);      /* ctx may be NULL: last create error */
 /* Run all work on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. torch's

@@ -72,6 +72,36 @@ def test_packer_layout():
     assert int(hb.seq2b[0]) == k
 
 
+def test_packer_random_sequences_and_offsets():
+    """fl_pack_sequence against a plain restatement of kmers.cpp:176-196 (any character, any length,
+    any offset -- the arena always uses multiples of 64, the packer itself takes any)."""
+    rng = np.random.default_rng(5)
+    L = capi.lib()
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKM-*", dtype=np.uint8)
+    code = np.zeros(256, dtype=np.uint32)
+    other = np.ones(256, dtype=np.uint32)
+    for i, ch in enumerate(b"AaCcGgTt"):
+        code[ch], other[ch] = i >> 1, 0
+    for trial in range(200):
+        n = int(rng.integers(0, 300))
+        off = int(rng.integers(0, 200)) if trial % 2 else 64 * int(rng.integers(0, 4))
+        seq = alphabet[rng.integers(0, len(alphabet), size=n)] if trial % 3 else rng.integers(1, 256, size=n).astype(np.uint8)
+        qual = rng.integers(33, 127, size=n).astype(np.uint8)
+        words = (off + n + 63) // 16 + 2
+        seq2b = np.zeros(words, dtype=np.uint32)
+        nmask = np.zeros(words, dtype=np.uint32)
+        qout = np.zeros(off + n + 64, dtype=np.uint8)
+        L.fl_pack_sequence(seq.tobytes(), qual.tobytes(), n, off, capi.ptr(seq2b), capi.ptr(qout), capi.ptr(nmask))
+        want2, wantm = np.zeros_like(seq2b), np.zeros_like(nmask)
+        for i in range(n):
+            b = off + i
+            want2[b >> 4] |= code[seq[i]] << np.uint32(30 - 2 * (b & 15))
+            wantm[b >> 5] |= other[seq[i]] << np.uint32(b & 31)
+        assert np.array_equal(seq2b, want2), (trial, n, off)
+        assert np.array_equal(nmask, wantm), (trial, n, off)
+        assert bytes(qout[off:off + n]) == qual.tobytes() and not qout[:off].any()
+
+
 def test_phred_tables_match_reference_formula():
     q = np.zeros(256)
     a = np.zeros(256)
