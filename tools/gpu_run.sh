@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_gpu_fullsize.py -x -q 2>&1 | tail -30) > gpurun_out/pytest_fullsize.log 2>&1
-cat gpurun_out/pytest_fullsize.log
+(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
 timeout 800 python tools/cli_e2e.py > gpurun_out/cli_e2e.json 2> gpurun_out/cli_e2e.err; tail -3 gpurun_out/cli_e2e.err
 python - <<'PY'
 import json
