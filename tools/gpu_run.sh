@@ -1,11 +1,7 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > gpurun_out/pytest_gpu.log 2>&1
-cat gpurun_out/pytest_gpu.log
-timeout 800 python tools/cli_e2e.py > gpurun_out/cli_e2e.json 2> gpurun_out/cli_e2e.err; tail -3 gpurun_out/cli_e2e.err
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/cli_e2e.json").read())
-for c in d["cases"]:
-    print(c["case"],c["bases"],c["stdout_identical"],c.get("speedup_wall"))
-    for k in ("reference_cpu","ours_gpu"): print("  ",k,c[k]["seconds"],c[k].get("phases"))
-PY
+timeout 600 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -2 gpurun_out/bench_c2.err; cut -c1-300 gpurun_out/bench_c2.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2.csv python bench.py --workload phred --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/launches_c2.out 2>&1
+timeout 600 python bench.py --workload kmer > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -2 gpurun_out/bench_c3.err; cut -c1-300 gpurun_out/bench_c3.json
+timeout 600 python bench.py --workload kmer --trim-split --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -2 gpurun_out/bench_c4.err; cut -c1-300 gpurun_out/bench_c4.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c4.csv python bench.py --workload kmer --trim-split --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/launches_c4.out 2>&1
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_c2_ref.json 2> gpurun_out/bench_c2_ref.err; tail -2 gpurun_out/bench_c2_ref.err; cut -c1-300 gpurun_out/bench_c2_ref.json
