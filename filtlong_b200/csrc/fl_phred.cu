@@ -643,14 +643,18 @@ __global__ void __launch_bounds__(PT_THREADS, 4) k_phred_sum(PhredArgs a, TieInf
                         break;
                     }
                     const int lx = __ffs(cross) - 1;
-                    double t = __longlong_as_double(cur + __shfl_sync(0xffffffffu, P - u, lx));   // exact sum before lane lx's part
-                    if ((int)lane == lx) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) t += *entry_of(tl, cw[k >> 2], k & 3);     // true adds (read.cpp:210-211)
-                    }
-                    t = shfl_d(t, lx);
-                    ce += 1;
+                    // one pass over the 16 bases for both jobs: lane lx continues from the exact sum before
+                    // its part with TRUE adds (read.cpp:210-211: this is where the sum leaves the binade),
+                    // the lanes after it redo their parts on the next binade's grid, anchored at 2 C
+                    const double t0 = __longlong_as_double(cur + __shfl_sync(0xffffffffu, P - u, lx));
                     C = C + C;
+                    ce += 1;
+                    double v = (int)lane == lx ? t0 : C;
+                    if ((int)lane >= lx) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v += *entry_of(tl, cw[k >> 2], k & 3);
+                    }
+                    const double t = shfl_d(v, lx);
                     bool hit = false;
                     if ((s_tie.any >> ce) & 1ull) hit = ((s_tie.many >> ce) & 1ull) || __any_sync(0xffffffffu, chunk_has<4>(cw, s_tie.ch[ce]));
                     if (hit || exponent_of(t) != ce || !(t == t) || round == 5) {
@@ -659,11 +663,7 @@ __global__ void __launch_bounds__(PT_THREADS, 4) k_phred_sum(PhredArgs a, TieInf
                     }
                     cur = __double_as_longlong(t);
                     lo = lx + 1;
-                    part = C;                                          // the lanes after lx on the coarser grid
-                    if ((int)lane >= lo) {
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) part += *entry_of(tl, cw[k >> 2], k & 3);
-                    }
+                    part = v;                                          // (only lanes >= lo are read)
                 }
                 if (!serial) tieflag = (s_tie.any >> e) & 1ull;
             }
