@@ -64,6 +64,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     // tuning knobs for profiling runs (defaults are the measured best, see profiles/ and DESIGN.md section 7)
     if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
+    if (const char *f = getenv("FL_ANCHOR")) c->anchor_enabled = atoi(f);
     if (const char *f = getenv("FL_PHRED_MODE")) c->phred_mode = atoi(f);
     if (const char *f = getenv("FL_PHRED_OCC")) c->phred_occupancy = atoi(f);
     {
@@ -92,6 +93,7 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     drain_timers(c);
     if (c->d_bitmap) cudaFree(c->d_bitmap);
     if (c->d_filter) cudaFree(c->d_filter);
+    if (c->d_anchor) cudaFree(c->d_anchor);
     for (int i = 0; i < 4; ++i) if (c->d_seen[i]) cudaFree(c->d_seen[i]);
     if (c->d_tfirst) cudaFree(c->d_tfirst);
     if (c->d_bittime) cudaFree(c->d_bittime);

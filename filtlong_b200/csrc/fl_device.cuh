@@ -95,6 +95,23 @@ __device__ __forceinline__ unsigned fl_length_bucket(int len) {
     return msb * 8 + frac;   // <= 31*8+7 = 255
 }
 
+// Position-anchored membership table (2 GiB, built from the bitmap by k_anchor_build). A random probe
+// of the 512 MiB bitmap costs a whole DRAM burst for one bit, and consecutive 16-mers of a read land in
+// unrelated words. But the four 16-mers starting at read positions 4g, 4g+1, 4g+2, 4g+3 all contain the
+// 13 bases at positions 4g+3 .. 4g+15: keyed by those 13 bases (26 bits), one 32-byte sector holds
+// everything the four probes need -- for each alignment r = 3 - (position & 3) a 64-bit quarter indexed
+// by the 3 remaining bases (the r bases before the key and the 3 - r after it). Every member of the set
+// is entered once per alignment (4x the bits of the bitmap), and a read's probes touch ONE sector per
+// four 16-mers instead of four.
+__device__ __forceinline__ void fl_anchor_slot(uint32_t kmer, unsigned r, uint32_t &word, uint32_t &bit) {
+    const unsigned sh = 6u - 2u * r;                                  // bits of the 3 - r bases after the key
+    const uint32_t key = (kmer >> sh) & 0x3FFFFFFu;                   // 13 bases
+    const uint32_t top = r ? (kmer >> (32u - 2u * r)) : 0u;           // the r bases before the key
+    const uint32_t rest = (top << sh) | (kmer & ((1u << sh) - 1u));   // 6 bits
+    word = key * 8u + r * 2u + (rest >> 5);
+    bit = rest & 31u;
+}
+
 // L2-resident pre-filter in front of the 512 MiB bitmap (fl_kmers.cu / fl_score.cu): two bits in ONE
 // 64-bit word of a 2^log2_words-word table. No false negatives, so "filter says absent" is final.
 // kind 1 picks the WORD from the k-mer's minimizer (smallest hashed 11-mer of its six): consecutive

@@ -107,6 +107,9 @@ struct fl_ctx {
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
     int filter_kind = 2;                 // bit 0: word from the k-mer minimizer instead of a plain hash; bit 1: load the filter with ld.global.cg (FL_FILTER_KIND)
     bool use_filter = false;
+    uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
+    bool use_anchor = false;
+    int anchor_enabled = 1;              // FL_ANCHOR=0 probes the bitmap itself (profiling, cross-checks)
     int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
     int filter_min_bits_per_key = 8;     // the filter is used while it has at least this many bits per member
     size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside granted to this context

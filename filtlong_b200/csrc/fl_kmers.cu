@@ -202,6 +202,25 @@ __global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict
     }
 }
 
+// anchored table build: every member of the bitmap is entered once per alignment (fl_anchor_slot)
+__global__ void __launch_bounds__(256) k_anchor_build(const uint32_t *__restrict__ bm, uint32_t *__restrict__ anchor) {
+    const size_t n_words = (size_t)1 << 27;
+    for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (size_t)gridDim.x * blockDim.x) {
+        uint32_t bits = bm[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t kmer = (uint32_t)(w << 5) | (uint32_t)b;
+#pragma unroll
+            for (unsigned r = 0; r < 4; ++r) {
+                uint32_t word, bit;
+                fl_anchor_slot(kmer, r, word, bit);
+                atomicOr(anchor + word, 1u << bit);
+            }
+        }
+    }
+}
+
 __global__ void k_contains(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ q, uint32_t n,
                            uint8_t *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,6 +319,16 @@ int fl_kmers_recount(fl_ctx *ctx) {
         if (!ctx->d_filter) FL_CUDA(ctx, cudaMalloc(&ctx->d_filter, filter_words * sizeof(unsigned long long)));
         FL_CUDA(ctx, cudaMemsetAsync(ctx->d_filter, 0, filter_words * sizeof(unsigned long long), ctx->stream));
         k_filter_build<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->d_bitmap, ctx->d_filter, ctx->filter_log2_words, ctx->filter_kind);
+        ctx->launches++;
+        FL_CUDA(ctx, cudaGetLastError());
+    }
+    // the table the probe kernel reads: one 32-byte sector per four consecutive 16-mers of a read
+    ctx->use_anchor = ctx->anchor_enabled && ctx->n_kmers > 0;
+    if (ctx->use_anchor) {
+        const size_t anchor_bytes = (size_t)1 << 31;
+        if (!ctx->d_anchor) FL_CUDA(ctx, cudaMalloc(&ctx->d_anchor, anchor_bytes));
+        FL_CUDA(ctx, cudaMemsetAsync(ctx->d_anchor, 0, anchor_bytes, ctx->stream));
+        k_anchor_build<<<(unsigned)ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->d_bitmap, ctx->d_anchor);
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
     }

@@ -41,6 +41,7 @@ struct ProbeArgs {
     uint32_t n;
     unsigned long long n_tiles;
     const uint32_t *bitmap;
+    const uint32_t *anchor;                  // position-anchored table (fl_anchor_slot), used when ANCH
     const unsigned long long *filter;        // L2-resident pre-filter (fl_kmers.cu), used when FILT
     unsigned filter_log2_words;
     int filter_kind;
@@ -64,9 +65,17 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     return p;
 }
 
+// word holding the membership bit of `kmer`, and the bit's index, for the k-mer that starts at a read
+// position whose low two bits are pos_lo2
+template <bool ANCH>
+__device__ __forceinline__ void probe_slot(uint32_t kmer, unsigned pos_lo2, uint32_t &word, uint32_t &bit) {
+    if (ANCH) fl_anchor_slot(kmer, 3u - pos_lo2, word, bit);
+    else { word = kmer >> 5; bit = kmer & 31u; }
+}
+
 template <int MODE>
-__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t kmer, unsigned long long pol_first) {
-    const uint32_t *p = bitmap + (kmer >> 5);
+__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t word_index, unsigned long long pol_first) {
+    const uint32_t *p = bitmap + word_index;
     if (MODE == 3) {
         uint32_t v;
         asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_first));
@@ -81,9 +90,10 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
     return __ldg(p);
 }
 
-template <int MODE, bool FILT>
+template <int MODE, bool FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
+    const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
     const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
     const unsigned long long pol_last = MODE == 3 ? l2_policy_evict_last() : 0ull;
     (void)pol_last;
@@ -107,7 +117,9 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                 unsigned long long b = tile_base - 16 + lane;
                 if (b + (FL_K - 1) < (unsigned long long)L) {
                     uint32_t k = __funnelshift_l(wb, wa, 2 * lane);
-                    hit = (probe<MODE>(a.bitmap, k, pol_first) >> (k & 31)) & 1u;
+                    uint32_t word, bit;
+                    probe_slot<ANCH>(k, lane & 3u, word, bit);         // tile_base is a multiple of 4
+                    hit = (probe<MODE>(table, word, pol_first) >> bit) & 1u;
                 }
             }
             carry = __ballot_sync(0xffffffffu, hit) << 16;
@@ -149,17 +161,50 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
                     }
                 }
+                if (ANCH) {
+                    // the four 16-mers starting at 4g .. 4g+3 of the lane's run (a multiple of 32, so of 4)
+                    // share one 32-byte sector of the anchored table: ONE 256-bit load per group
+                    uint32_t sec[4][8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int p = half * 16 + i;
-                    const uint32_t k = fl_kmer_at(w, p);
-                    words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(a.bitmap, k, pol_first) : 0u;     // read.cpp:52
-                }
+                    for (int g = 0; g < 4; ++g) {
+                        const int p0 = half * 16 + 4 * g;
+                        const uint32_t key = (fl_kmer_at(w, p0 + 3) >> 6) & 0x3FFFFFFu;   // bases p0+3 .. p0+15
+                        const bool need = p0 < nvalid && ((go >> (4 * g)) & 0xFu);
+                        if (need) {
+                            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                           "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                         : "l"(table + (size_t)key * 8u));
+                        } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int p = half * 16 + i;
-                    const uint32_t k = fl_kmer_at(w, p);
-                    h |= ((words[i] >> (k & 31)) & 1u) << p;
+                            for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int p = half * 16 + 4 * g + j;
+                            uint32_t word, bit;
+                            fl_anchor_slot(fl_kmer_at(w, p), 3u - (unsigned)j, word, bit);
+                            const uint32_t v = (word & 1u) ? sec[g][2 * (3 - j) + 1] : sec[g][2 * (3 - j)];
+                            const uint32_t ok = (p < nvalid && ((go >> (4 * g + j)) & 1u)) ? 1u : 0u;
+                            h |= (((v >> bit) & 1u) & ok) << p;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = half * 16 + i;
+                        const uint32_t k = fl_kmer_at(w, p);
+                        words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(table, k >> 5, pol_first) : 0u;     // read.cpp:52
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = half * 16 + i;
+                        const uint32_t k = fl_kmer_at(w, p);
+                        h |= ((words[i] >> (k & 31)) & 1u) << p;
+                    }
                 }
             }
             // paint: base covered if any of the 16 k-mers ending at or after it hit (read.cpp:53-54)
@@ -539,7 +584,7 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     if (n_tiles) {
         ProbeArgs pa{};
         pa.seq2b = b.seq2b; pa.off = b.off; pa.len = b.len; pa.tile_start = ctx->sc_u64a.p;
-        pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.mask = ctx->sc_mask.p;
+        pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.anchor = ctx->d_anchor; pa.mask = ctx->sc_mask.p;
         pa.filter = ctx->d_filter; pa.filter_log2_words = ctx->filter_log2_words; pa.filter_kind = ctx->filter_kind;
         unsigned blocks = (unsigned)((n_tiles + 7) / 8);
         unsigned max_blocks = (unsigned)ctx->sm_count * 4;
@@ -558,19 +603,22 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
             }
-            if (ctx->use_filter) {
+            if (ctx->use_anchor) {
+                if (ctx->use_filter) k_probe_paint<2, true, true><<<blocks, 256, 0, st>>>(pa);
+                else k_probe_paint<2, false, true><<<blocks, 256, 0, st>>>(pa);
+            } else if (ctx->use_filter) {
                 switch (ctx->probe_mode) {
-                    case 0: k_probe_paint<0, true><<<blocks, 256, 0, st>>>(pa); break;
-                    case 2: k_probe_paint<2, true><<<blocks, 256, 0, st>>>(pa); break;
-                    case 3: k_probe_paint<3, true><<<blocks, 256, 0, st>>>(pa); break;
-                    default: k_probe_paint<1, true><<<blocks, 256, 0, st>>>(pa); break;
+                    case 0: k_probe_paint<0, true, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 2: k_probe_paint<2, true, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 3: k_probe_paint<3, true, false><<<blocks, 256, 0, st>>>(pa); break;
+                    default: k_probe_paint<1, true, false><<<blocks, 256, 0, st>>>(pa); break;
                 }
             } else {
                 switch (ctx->probe_mode) {
-                    case 0: k_probe_paint<0, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 2: k_probe_paint<2, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 3: k_probe_paint<3, false><<<blocks, 256, 0, st>>>(pa); break;
-                    default: k_probe_paint<1, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 0: k_probe_paint<0, false, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 2: k_probe_paint<2, false, false><<<blocks, 256, 0, st>>>(pa); break;
+                    case 3: k_probe_paint<3, false, false><<<blocks, 256, 0, st>>>(pa); break;
+                    default: k_probe_paint<1, false, false><<<blocks, 256, 0, st>>>(pa); break;
                 }
             }
             if (persist) {

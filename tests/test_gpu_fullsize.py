@@ -2,8 +2,8 @@
 10 Mbp assembly), where the oracle cannot follow. Parity is carried by size-independent properties:
 
 * two independent exact implementations of the same scores must agree bit-for-bit on every one of
-  the 2 M reads (Phred: lattice warp kernels vs one-thread-per-chain work items; k-mer: probe with
-  and without the L2 pre-filter);
+  the 2 M reads (Phred: lattice warp kernels vs one-thread-per-chain work items; k-mer: the position-anchored
+  table with and without the L2 pre-filter, and the plain bitmap);
 * results must not depend on how the read set is cut into batches;
 * the first few thousand reads, regenerated on the host with the same counter-based generator,
   must match the oracle bit-for-bit;
@@ -140,8 +140,8 @@ def test_config3_kmer_full_size():
 
     keep = [as_torch(w[k]) for k in ("start", "strand", "err", "junk_pos", "junk_len")]
     results = {}
-    for tag, filt in (("filter", 1), ("direct", 0)):
-        with _env(FL_FILTER=filt):
+    for tag, filt, anch in (("filter", 1, 1), ("direct", 0, 1), ("bitmap", 1, 0)):
+        with _env(FL_FILTER=filt, FL_ANCHOR=anch):
             ctx = api.Context(params)
         if tag == "filter":
             capi.check(ctx.h, L.fl_synth_genome_device(ctx.h, w["genome_seed"], gb, d_genome.data_ptr()), "synth_genome")
@@ -161,15 +161,17 @@ def test_config3_kmer_full_size():
         results[tag] = (ctx.read_results(), ctx.row_results(), summ, n_kmers)
         ctx.close()
     rr, rows, summ, n_kmers = results["filter"]
-    r2, rows2, s2, n2 = results["direct"]
-    assert n_kmers == n2 and 19 * 10 ** 6 < n_kmers <= 2 * (gb - 15)
-    for k in ("mean_q", "window_q"):
-        assert np.array_equal(rr[k].view(np.uint64), r2[k].view(np.uint64)), k
-    for k in ("first_base_in_kmer", "last_base_in_kmer", "n_bad", "n_child", "passed"):
-        assert np.array_equal(rr[k], r2[k]), k
-    for k in ("start", "end", "passed_final"):
-        assert np.array_equal(rows[k], rows2[k]), k
-    assert (s2.status, s2.target, s2.keeping) == (summ.status, summ.target, summ.keeping)
+    assert 19 * 10 ** 6 < n_kmers <= 2 * (gb - 15)
+    for other in ("direct", "bitmap"):
+        r2, rows2, s2, n2 = results[other]
+        assert n_kmers == n2
+        for k in ("mean_q", "window_q"):
+            assert np.array_equal(rr[k].view(np.uint64), r2[k].view(np.uint64)), (other, k)
+        for k in ("first_base_in_kmer", "last_base_in_kmer", "n_bad", "n_child", "passed"):
+            assert np.array_equal(rr[k], r2[k]), (other, k)
+        for k in ("start", "end", "passed_final"):
+            assert np.array_equal(rows[k], rows2[k]), (other, k)
+        assert (s2.status, s2.target, s2.keeping) == (summ.status, summ.target, summ.keeping)
     # children tile their parent without overlap, in coordinate order (read.cpp:119-130)
     assert np.all(rows["end"] >= rows["start"])
     same_parent = rows["parent"][1:] == rows["parent"][:-1]
