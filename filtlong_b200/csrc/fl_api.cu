@@ -3,7 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 
-#include "fl_internal.cuh"
+#include "fl_device.cuh"
 
 static std::string g_create_error;
 static void drain_timers(fl_ctx *c);
@@ -171,6 +171,13 @@ extern "C" int fl_ctx_kernel_time(fl_ctx *c, int which, double *total_ms, uint64
 // ---------------------------------------------------------------------------------------------
 // host packer
 // ---------------------------------------------------------------------------------------------
+extern "C" void fl_anchor_slot_host(uint32_t kmer, uint32_t pos_lo2, uint32_t *word, uint32_t *bit) {
+    uint32_t w = 0, b = 0;
+    fl_anchor_slot(kmer, 3u - (pos_lo2 & 3u), w, b);
+    if (word) *word = w;
+    if (bit) *bit = b;
+}
+
 extern "C" uint64_t fl_padded_len(int64_t len) {
     if (len <= 0) return 0;
     return ((uint64_t)len + FL_ALIGN_BASES - 1) & ~(uint64_t)(FL_ALIGN_BASES - 1);

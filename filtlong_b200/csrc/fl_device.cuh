@@ -103,7 +103,7 @@ __device__ __forceinline__ unsigned fl_length_bucket(int len) {
 // by the 3 remaining bases (the r bases before the key and the 3 - r after it). Every member of the set
 // is entered once per alignment (4x the bits of the bitmap), and a read's probes touch ONE sector per
 // four 16-mers instead of four.
-__device__ __forceinline__ void fl_anchor_slot(uint32_t kmer, unsigned r, uint32_t &word, uint32_t &bit) {
+__host__ __device__ __forceinline__ void fl_anchor_slot(uint32_t kmer, unsigned r, uint32_t &word, uint32_t &bit) {
     const unsigned sh = 6u - 2u * r;                                  // bits of the 3 - r bases after the key
     const uint32_t key = (kmer >> sh) & 0x3FFFFFFu;                   // 13 bases
     const uint32_t top = r ? (kmer >> (32u - 2u * r)) : 0u;           // the r bases before the key

@@ -103,6 +103,11 @@ int fl_ctx_enable_timing(fl_ctx *ctx, int on);
 int fl_ctx_reset_timing(fl_ctx *ctx);
 int fl_ctx_kernel_time(fl_ctx *ctx, int which, double *total_ms, uint64_t *launches);
 
+/* Test hook (host): where the probe kernel looks for `kmer` when the 16-mer starts at a read position
+ * whose low two bits are pos_lo2 -- 32-bit word index into the 2 GiB position-anchored table and the
+ * bit inside it. Four consecutive 16-mers of a read share one 32-byte sector. */
+void fl_anchor_slot_host(uint32_t kmer, uint32_t pos_lo2, uint32_t *word, uint32_t *bit);
+
 /* ---- host-side packer (replaces the char* hand-off of read.h:32 / kmers.cpp:96-121) ------- */
 /* Padded size of a sequence of `len` bases. */
 uint64_t fl_padded_len(int64_t len);

@@ -102,6 +102,45 @@ def test_packer_random_sequences_and_offsets():
         assert bytes(qout[off:off + n]) == qual.tobytes() and not qout[:off].any()
 
 
+def test_anchored_table_mapping():
+    """The position-anchored probe table: the four 16-mers starting at read positions
+    4g .. 4g+3 fall into ONE 32-byte sector (8 words), into four different 64-bit quarters, and the map
+    (16-mer, alignment) -> bit is injective (no two members share a bit, so membership stays exact)."""
+    L = capi.lib()
+    rng = np.random.default_rng(9)
+
+    def slot(kmer, pos):
+        w, b = C.c_uint32(), C.c_uint32()
+        L.fl_anchor_slot_host(int(kmer), pos & 3, C.byref(w), C.byref(b))
+        return w.value, b.value
+
+    code = rng.integers(0, 4, size=4000)
+    kmers = []
+    for i in range(len(code) - 15):
+        k = 0
+        for c in code[i:i + 16]:
+            k = (k << 2) | int(c)
+        kmers.append(k)
+    for g in range(0, len(kmers) - 3, 4):
+        slots = [slot(kmers[g + j], g + j) for j in range(4)]
+        assert len({w >> 3 for w, _ in slots}) == 1                       # one sector
+        assert sorted((w & 7) >> 1 for w, _ in slots) == [0, 1, 2, 3]    # a quarter per alignment
+        assert all(w < (1 << 29) and b < 32 for w, b in slots)
+    # injective per alignment: invert the slot back to the 16-mer
+    for _ in range(2000):
+        k = int(rng.integers(0, 1 << 32))
+        for pos in range(4):
+            w, b = slot(k, pos)
+            r = 3 - pos
+            key, q = w >> 3, (w & 7) >> 1
+            rest = ((w & 1) << 5) | b
+            assert q == r
+            sh = 6 - 2 * r
+            top, bottom = rest >> sh, rest & ((1 << sh) - 1)
+            back = ((top << (32 - 2 * r)) if r else 0) | (key << sh) | bottom
+            assert back == k
+
+
 def test_phred_tables_match_reference_formula():
     q = np.zeros(256)
     a = np.zeros(256)
