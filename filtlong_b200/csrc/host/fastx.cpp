@@ -15,6 +15,7 @@ int FastxReader::getc() {
     if (err_) return -3;
     if (eof_ && begin_ >= end_) return -1;
     if (begin_ >= end_) {
+        buf_base_ += (uint64_t)end_;
         begin_ = 0;
         end_ = gzread(fp_, buf_, kBuf);
         if (end_ == 0) { eof_ = true; return -1; }
@@ -30,6 +31,7 @@ bool FastxReader::get_line(std::string &s, bool append) {
         if (err_) return false;
         if (begin_ >= end_) {
             if (eof_) break;
+            buf_base_ += (uint64_t)end_;
             begin_ = 0;
             end_ = gzread(fp_, buf_, kBuf);
             if (end_ == 0) { eof_ = true; break; }
@@ -43,7 +45,8 @@ bool FastxReader::get_line(std::string &s, bool append) {
         if (i < end_) break;   // newline consumed
     }
     if (!gotany && eof_) return false;
-    if (s.size() > 1 && s.back() == '\r') s.pop_back();
+    stripped_cr_ = false;
+    if (s.size() > 1 && s.back() == '\r') { s.pop_back(); stripped_cr_ = true; }
     return true;
 }
 
@@ -68,12 +71,21 @@ int64_t FastxReader::next() {
         name.push_back((char)c);
     }
     if (!got) return c == -3 ? -3 : -1;
-    if (c >= 0 && c != '\n') get_line(comment, false);
+    simple = true;
+    comment_off = pos();
+    if (c >= 0 && c != '\n') {
+        get_line(comment, false);
+        if (stripped_cr_) simple = false;
+    }
+    int seq_lines = 0;
     while ((c = getc()) >= 0 && c != '>' && c != '+' && c != '@') {
         if (c == '\n') continue;
+        if (seq_lines++ == 0) seq_off = pos() - 1;
         seq.push_back((char)c);
         get_line(seq, true);
+        if (stripped_cr_) simple = false;
     }
+    if (seq_lines != 1) simple = false;
     if (c == '>' || c == '@') last_char_ = c;
     is_fastq = (c == '+');
     if (!is_fastq) {
@@ -82,7 +94,14 @@ int64_t FastxReader::next() {
     }
     while ((c = getc()) >= 0 && c != '\n') {}
     if (c == -1) return -2;
-    while (get_line(qual, true) && qual.size() < seq.size()) {}
+    qual_off = pos();
+    int qual_lines = 0;
+    while (get_line(qual, true)) {
+        ++qual_lines;
+        if (stripped_cr_) simple = false;
+        if (qual.size() >= seq.size()) break;
+    }
+    if (qual_lines != 1) simple = false;
     if (err_) return -3;
     last_char_ = 0;
     if (seq.size() != qual.size()) return -2;

@@ -26,6 +26,16 @@ public:
     std::string name, comment, seq, qual;
     bool is_fastq = false;
 
+    // Where the last record sits in the (uncompressed) byte stream, for writers that want to copy
+    // slices of the input instead of parsing it a second time (main.cpp:263-313 re-reads the file).
+    // Valid after next() >= 0. `simple` says the sequence and the quality each came from exactly one
+    // line with nothing stripped, i.e. input[seq_off, seq_off + length) IS the sequence (and likewise
+    // for the quality and the comment); otherwise the offsets must not be used.
+    bool simple = false;
+    uint64_t comment_off = 0, seq_off = 0, qual_off = 0;
+    // true when the file is not compressed: stream offsets are file offsets
+    bool plain() const { return fp_ && gzdirect(fp_) != 0; }
+
 private:
     int getc();
     // appends the rest of the current line to s (without the newline); returns false at EOF with
@@ -35,6 +45,9 @@ private:
     static constexpr int kBuf = 1 << 16;
     unsigned char *buf_;
     int begin_ = 0, end_ = 0;
+    uint64_t buf_base_ = 0;            // stream offset of buf_[0]
+    bool stripped_cr_ = false;         // the last get_line dropped a '\r'
+    uint64_t pos() const { return buf_base_ + (uint64_t)begin_; }
     bool eof_ = false, err_ = false;
     int last_char_ = 0;
 };

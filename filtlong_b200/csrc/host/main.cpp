@@ -5,6 +5,10 @@
 // scored on the GPU batch by batch (instead of one `new Read` per record, main.cpp:108), and the
 // normalise / sort / threshold block (main.cpp:169-261) is one fl_finalize call. Pass 2 re-reads
 // the input and prints the survivors exactly like main.cpp:263-313.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <chrono>
@@ -85,6 +89,12 @@ int main(int argc, char **argv) {
         reads.reserve(kBatchBases + (4ull << 20), 1u << 18);
         unsigned long long queued = 0;
         size_t verbose_done = 0;
+        // where each record's comment / sequence / quality sit in the input, when the reader can vouch
+        // for it (uncompressed file, single-line records): pass 2 then copies slices of the mapped file
+        // instead of parsing it a second time
+        bool slices_ok = true;
+        std::vector<uint64_t> rec_comment_off, rec_seq_off, rec_qual_off;
+        std::vector<uint32_t> rec_comment_len;
         auto verbose_flush = [&]() {
             if (!args.verbose) return;
             reads.download();
@@ -122,6 +132,17 @@ int main(int argc, char **argv) {
                 if (fasta_format && kmers_empty) {
                     std::cerr << "\n\n" << "Error: FASTA input not supported without an external reference" << "\n";
                     return 1;
+                }
+                if (slices_ok) {
+                    if (in.simple && in.plain() && in.comment.size() < (1u << 31)) {
+                        rec_comment_off.push_back(in.comment_off);
+                        rec_comment_len.push_back((uint32_t)in.comment.size());
+                        rec_seq_off.push_back(in.seq_off);
+                        rec_qual_off.push_back(in.qual_off);
+                    } else {
+                        slices_ok = false;
+                        rec_comment_off.clear(); rec_comment_len.clear(); rec_seq_off.clear(); rec_qual_off.clear();
+                    }
                 }
                 // Phred mode needs a quality byte per base; an empty record has neither
                 reads.add(in.name, in.seq.data(), in.qual.empty() ? (kmers_empty ? "" : nullptr) : in.qual.data(), (int)in.seq.size());
@@ -184,7 +205,59 @@ int main(int argc, char **argv) {
 
         // ---- pass 2: output the keepers in input order (main.cpp:263-313) ----
         std::cerr << "Outputting passed long reads\n";
-        {
+        bool printed = false;
+        if (slices_ok && rec_seq_off.size() == reads.n_reads() && reads.n_reads() > 0) {
+            // same bytes as the loop below, taken from the mapped input at the offsets pass 1 recorded
+            const int fd = open(args.input_reads.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd >= 0 && fstat(fd, &st) == 0 && st.st_size > 0) {
+                void *mp = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (mp != MAP_FAILED) {
+                    const char *base = (const char *)mp;
+                    const uint64_t fsize = (uint64_t)st.st_size;
+                    bool in_bounds = true;
+                    for (size_t i = 0; i < reads.n_reads() && in_bounds; ++i) {
+                        const uint64_t L = (uint64_t)reads.length[i];
+                        in_bounds = rec_seq_off[i] + L <= fsize && (!fastq_output || rec_qual_off[i] + L <= fsize) &&
+                                    rec_comment_off[i] + rec_comment_len[i] <= fsize;
+                    }
+                    if (in_bounds) {
+                        std::string out;
+                        out.reserve(1 << 20);
+                        auto emit = [&](size_t i, const std::string &nm, int start, int length) {
+                            out += fasta_output ? '>' : '@';
+                            out += nm;
+                            if (rec_comment_len[i]) { out += ' '; out.append(base + rec_comment_off[i], rec_comment_len[i]); }
+                            out += '\n';
+                            out.append(base + rec_seq_off[i] + start, (size_t)length);
+                            out += '\n';
+                            if (fastq_output) { out += "+\n"; out.append(base + rec_qual_off[i] + start, (size_t)length); out += '\n'; }
+                        };
+                        for (size_t i = 0; i < reads.n_reads(); ++i) {
+                            const size_t rs = (size_t)reads.row_start[i];
+                            if (reads.n_child[i] == 0) {
+                                if (reads.row_pfinal[rs]) emit(i, reads.names[i], 0, reads.length[i]);
+                            } else {
+                                for (int c = 0; c < reads.n_child[i]; ++c) {
+                                    const size_t row = rs + (size_t)c;
+                                    if (!reads.row_pfinal[row]) continue;
+                                    const int start = reads.row_s[row], length = reads.row_e[row] - reads.row_s[row];
+                                    if (length <= 0) continue;
+                                    emit(i, reads.row_name(row), start, length);
+                                }
+                            }
+                            if (out.size() >= (1 << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+                        }
+                        fwrite(out.data(), 1, out.size(), stdout);
+                        fflush(stdout);
+                        printed = true;
+                    }
+                    munmap(mp, (size_t)st.st_size);
+                }
+            }
+            if (fd >= 0) close(fd);
+        }
+        if (!printed) {
             FastxReader in(args.input_reads);
             size_t i = 0;
             std::string out;

@@ -1,10 +1,12 @@
 mkdir -p gpurun_out
-timeout 300 python bench.py --steps 5 --no-cpu-baseline > gpurun_out/bench_c2_chk.json 2> gpurun_out/bench_c2_chk.err; tail -2 gpurun_out/bench_c2_chk.err
-timeout 300 python bench.py --workload kmer --steps 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_c3_chk.json 2> gpurun_out/bench_c3_chk.err; tail -2 gpurun_out/bench_c3_chk.err
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 500 python tools/cli_e2e.py > gpurun_out/cli_e2e.json 2> gpurun_out/cli_e2e.err; tail -3 gpurun_out/cli_e2e.err
 python - <<'PY'
 import json
-for f in ('bench_c2_chk','bench_c3_chk'):
-    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1])
-    print(f, round(d['value'],1), round(d['ms_per_step'],2), d['roofline']['traffic'], round(d['roofline']['frac'],3), d['e2e'] and round(d['e2e']['value'],1))
+d=json.loads(open("gpurun_out/cli_e2e.json").read())
+for c in d["cases"]:
+    print(c["case"],c["bases"],c["stdout_identical"],c.get("speedup_wall"))
+    for k in ("reference_cpu","ours_gpu"): print("  ",k,c[k]["seconds"],c[k].get("phases"))
 PY
-timeout 600 python tools/kbuild_bench.py > gpurun_out/kbuild.jsonl 2> gpurun_out/kbuild.err; tail -3 gpurun_out/kbuild.err; cut -c1-700 gpurun_out/kbuild.jsonl
