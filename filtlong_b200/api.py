@@ -41,13 +41,14 @@ class HostBatch:
         return b
 
 
-def device_batch(n, padded_bases, off, length, seq2b=None, qual=None, nmask=None):
+def device_batch(n, padded_bases, off, length, seq2b=None, qual=None, nmask=None, ascii=None):
     """fl_batch whose pointers are device pointers (torch tensors or raw ints)."""
     b = capi.Batch()
     b.n = n
     b.padded_bases = padded_bases
     b.off, b.len = capi.ptr(off), capi.ptr(length)
     b.seq2b, b.qual, b.nmask = capi.ptr(seq2b), capi.ptr(qual), capi.ptr(nmask)
+    b.ascii = capi.ptr(ascii)
     return b
 
 
@@ -146,6 +147,33 @@ class Context:
 
     def kmers_release_build_state(self):
         self._ck(self.L.fl_kmers_release_build_state(self.h), "fl_kmers_release_build_state")
+
+    # ---- sharded read set (one context per GPU, NCCL behind the C ABI) ----
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        rc = capi.lib().fl_comm_unique_id(buf)
+        if rc != 0:
+            raise FLError("fl_comm_unique_id failed (%d): NCCL not available" % rc)
+        return bytes(buf)
+
+    def comm_init(self, id128, rank, nranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(self.L.fl_comm_init(self.h, buf, rank, nranks), "fl_comm_init")
+
+    def comm_destroy(self):
+        self._ck(self.L.fl_comm_destroy(self.h), "fl_comm_destroy")
+
+    def kmers_broadcast(self, root=0):
+        self._ck(self.L.fl_kmers_broadcast(self.h, root), "fl_kmers_broadcast")
+
+    def allreduce_i64(self, values):
+        a = np.ascontiguousarray(values, dtype=np.int64)
+        self._ck(self.L.fl_comm_allreduce_i64_host(self.h, capi.ptr(a), a.size), "fl_comm_allreduce_i64_host")
+        return a
+
+    def collective_count(self):
+        return int(self.L.fl_comm_collective_count(self.h))
 
     # ---- Read (read.h:29-65) ----
     def push(self, host_batch):

@@ -63,7 +63,7 @@ class Batch(C.Structure):
     _fields_ = [
         ("n", C.c_uint32), ("reserved", C.c_uint32), ("padded_bases", C.c_uint64),
         ("off", C.c_void_p), ("len", C.c_void_p), ("seq2b", C.c_void_p), ("qual", C.c_void_p),
-        ("nmask", C.c_void_p),
+        ("nmask", C.c_void_p), ("ascii", C.c_void_p),
     ]
 
 
@@ -90,10 +90,14 @@ class RowResults(C.Structure):
 
 class SynthReads(C.Structure):
     _fields_ = [
-        ("n", C.c_uint32), ("reserved", C.c_uint32), ("genome_bases", C.c_uint64),
+        ("n", C.c_uint32), ("flags", C.c_uint32), ("genome_bases", C.c_uint64),
         ("off", C.c_void_p), ("len", C.c_void_p), ("start", C.c_void_p), ("strand", C.c_void_p),
         ("err_ppm", C.c_void_p), ("junk_pos", C.c_void_p), ("junk_len", C.c_void_p),
+        ("adap5", C.c_void_p), ("adap3", C.c_void_p),
     ]
+
+
+SYNTH_INDELS = 1
 
 
 # every symbol include/filtlong_b200.h declares: (name, restype, argtypes)
@@ -139,12 +143,23 @@ SYMBOLS = [
     ("fl_results_rows", C.c_int, [_P, C.POINTER(RowResults)]),
     ("fl_results_pass_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("fl_results_pass", C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("fl_comm_unique_id", C.c_int, [_P]),
+    ("fl_comm_init", C.c_int, [_P, _P, C.c_int, C.c_int]),
+    ("fl_comm_destroy", C.c_int, [_P]),
+    ("fl_comm_info", C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("fl_kmers_broadcast", C.c_int, [_P, C.c_int]),
+    ("fl_comm_allreduce_i64_host", C.c_int, [_P, _P, C.c_int]),
+    ("fl_comm_collective_count", C.c_uint64, [_P]),
     ("fl_synth_qual_device", C.c_int, [_P, C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64, _P]),
     ("fl_synth_qual_host", None, [C.c_uint64, C.c_uint32, _P, _P, _P, C.c_uint64, _P]),
     ("fl_synth_genome_device", C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
     ("fl_synth_genome_host", None, [C.c_uint64, C.c_uint64, _P]),
     ("fl_synth_reads_device", C.c_int, [_P, C.c_uint64, _P, C.POINTER(SynthReads), C.c_uint64, _P]),
     ("fl_synth_reads_host", None, [C.c_uint64, _P, C.POINTER(SynthReads), C.c_uint64, _P]),
+    ("fl_synth_assembly_device", C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P]),
+    ("fl_synth_assembly_host", None, [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, _P, _P]),
+    ("fl_synth_ascii_device", C.c_int, [_P, C.c_uint32, _P, _P, _P, _P, _P]),
+    ("fl_synth_ascii_host", None, [C.c_uint32, _P, _P, _P, _P, _P]),
     ("fl_version", C.c_char_p, []),
     ("fl_phred_luts", None, [C.c_int32, _P, _P]),
 ]
@@ -166,6 +181,25 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+SYNTH_LIB_PATH = os.path.join(PKG, "libflsynth_host.so")
+_synth = None
+
+
+def synth_host_lib():
+    """The host-only synthetic generators (libflsynth_host.so, no CUDA inside): what the CPU legs of
+    bench.py use to write their sample files, so that they never map the CUDA library."""
+    global _synth
+    if _synth is None:
+        L = C.CDLL(SYNTH_LIB_PATH)
+        for name, res, args in SYMBOLS:
+            if name.startswith("fl_synth_") and name.endswith("_host"):
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+        _synth = L
+    return _synth
 
 
 def check(ctx_handle, rc, what):

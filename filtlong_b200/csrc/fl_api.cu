@@ -110,20 +110,20 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
 }
 
 extern "C" int fl_ctx_set_stream(fl_ctx *c, void *cuda_stream) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_CUDA(c, cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return FL_OK;
 }
 
 extern "C" int fl_ctx_sync(fl_ctx *c) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_CUDA(c, cudaStreamSynchronize(c->stream));
     return FL_OK;
 }
 
 extern "C" int fl_ctx_set_params(fl_ctx *c, const fl_params *p) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     std::string why;
     if (validate_params(p, why) != FL_OK) { c->set_error(why); return FL_EINVAL; }
     c->p = *p;
@@ -146,13 +146,13 @@ static void drain_timers(fl_ctx *c) {
 }
 
 extern "C" int fl_ctx_enable_timing(fl_ctx *c, int on) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     c->timing = on != 0;
     return FL_OK;
 }
 
 extern "C" int fl_ctx_reset_timing(fl_ctx *c) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_CUDA(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
     for (int i = 0; i < FL_KERNEL_COUNT; ++i) { c->kernel_ms[i] = 0; c->kernel_launches[i] = 0; }
@@ -161,6 +161,7 @@ extern "C" int fl_ctx_reset_timing(fl_ctx *c) {
 
 extern "C" int fl_ctx_kernel_time(fl_ctx *c, int which, double *total_ms, uint64_t *launches) {
     if (!c || which < 0 || which >= FL_KERNEL_COUNT) return FL_EINVAL;
+    FL_ENTER(c);
     FL_CUDA(c, cudaStreamSynchronize(c->stream));
     drain_timers(c);
     if (total_ms) *total_ms = c->kernel_ms[which];
@@ -235,6 +236,53 @@ extern "C" void fl_phred_luts(int32_t window_size, double *q256, double *a256) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// device-side packer: text -> 2-bit codes (kmers.cpp:176-196: A/a 0, C/c 1, G/g 2, T/t 3, anything else 0)
+// and the non-ACGT mask reference sequences need (kmers.cpp:199-219). A pure stream over the arena: one
+// thread per 32 bases (two 16-byte loads -> two sequence words + one mask word). Padding bytes produce
+// arbitrary codes; no kernel ever forms a 16-mer from bases at or beyond a sequence's length.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &other4) {
+    x &= 0xDFDFDFDFu;                                     // fold lower case onto upper case
+    const uint32_t mA = __vcmpeq4(x, 0x41414141u), mC = __vcmpeq4(x, 0x43434343u), mG = __vcmpeq4(x, 0x47474747u),
+                   mT = __vcmpeq4(x, 0x54545454u);
+    const uint32_t v = ((mC | mT) & 0x01010101u) | ((mG | mT) & 0x02020202u);      // 2-bit code in every byte
+    code8 = (v * 0x40100401u) >> 24;                       // first character in bits 7:6 (no carries: fields never overlap)
+    const uint32_t o = ~(mA | mC | mG | mT) & 0x01010101u;
+    other4 = (o | (o >> 7) | (o >> 14) | (o >> 21)) & 0xFu; // first character in bit 0
+}
+
+__global__ void __launch_bounds__(256) k_pack_ascii(const uint8_t *__restrict__ ascii, unsigned long long groups,
+                                                    uint32_t *__restrict__ seq2b, uint32_t *__restrict__ nmask) {
+    const uint4 *in = reinterpret_cast<const uint4 *>(ascii);
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(in + 2 * g), b = __ldg(in + 2 * g + 1);
+        const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t w[2] = {0u, 0u}, m = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t code8, other4;
+            pack4(c[i], code8, other4);
+            w[i >> 2] |= code8 << (24 - 8 * (i & 3));
+            m |= other4 << (4 * i);
+        }
+        reinterpret_cast<uint2 *>(seq2b)[g] = make_uint2(w[0], w[1]);
+        if (nmask) nmask[g] = m;
+    }
+}
+
+int fl_pack_ascii_device(fl_ctx *c, const uint8_t *ascii, uint64_t padded_bases, uint32_t *seq2b, uint32_t *nmask, cudaStream_t s) {
+    const unsigned long long groups = padded_bases >> 5;
+    if (!groups) return FL_OK;
+    unsigned blocks = fl_blocks(groups, 256);
+    if (blocks > (unsigned)c->sm_count * 16) blocks = (unsigned)c->sm_count * 16;
+    k_pack_ascii<<<blocks, 256, 0, s>>>(ascii, groups, seq2b, nmask);
+    c->launches++;
+    FL_CUDA(c, cudaGetLastError());
+    return FL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // batches
 // ---------------------------------------------------------------------------------------------
 static int check_batch(fl_ctx *c, const fl_batch *b) {
@@ -256,19 +304,29 @@ static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool wan
     v->padded_bases = h->padded_bases;
     v->off = S.off.p;
     v->len = S.len.p;
-    v->seq2b = nullptr; v->qual = nullptr; v->nmask = nullptr;
+    v->seq2b = nullptr; v->qual = nullptr; v->nmask = nullptr; v->ascii = nullptr;
     if (want_seq && h->seq2b) {
         size_t words = (size_t)(h->padded_bases >> 4);
         FL_CUDA(c, S.seq.reserve(words + 4, 0, s));
         FL_CUDA(c, cudaMemcpyAsync(S.seq.p, h->seq2b, words * 4, cudaMemcpyHostToDevice, s));
         v->seq2b = S.seq.p;
+    } else if (want_seq && h->ascii) {
+        // text hand-off (read.h:32 / kmers.cpp:96-121): copy the bytes, pack on the device
+        size_t words = (size_t)(h->padded_bases >> 4);
+        FL_CUDA(c, S.ascii.reserve((size_t)h->padded_bases + 64, 0, s));
+        FL_CUDA(c, S.seq.reserve(words + 4, 0, s));
+        if (want_nmask) FL_CUDA(c, S.nmask.reserve((words >> 1) + 4, 0, s));
+        FL_CUDA(c, cudaMemcpyAsync(S.ascii.p, h->ascii, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
+        FL_TRY(fl_pack_ascii_device(c, S.ascii.p, h->padded_bases, S.seq.p, want_nmask ? S.nmask.p : nullptr, s));
+        v->seq2b = S.seq.p;
+        if (want_nmask) v->nmask = S.nmask.p;
     }
     if (want_qual && h->qual) {
         FL_CUDA(c, S.qual.reserve((size_t)h->padded_bases + 64, 0, s));
         FL_CUDA(c, cudaMemcpyAsync(S.qual.p, h->qual, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
         v->qual = S.qual.p;
     }
-    if (want_nmask && h->nmask) {
+    if (want_nmask && h->nmask && h->seq2b) {
         size_t words = (size_t)(h->padded_bases >> 5);
         FL_CUDA(c, S.nmask.reserve(words + 4, 0, s));
         FL_CUDA(c, cudaMemcpyAsync(S.nmask.p, h->nmask, words * 4, cudaMemcpyHostToDevice, s));
@@ -286,15 +344,25 @@ static int staging_acquire(fl_ctx *c, int slot) {
     return FL_OK;
 }
 
-static BatchView view_of_device_batch(const fl_batch *b) {
+static int view_of_device_batch(fl_ctx *c, const fl_batch *b, bool want_nmask, BatchView *out) {
     BatchView v{};
     v.n = b->n; v.padded_bases = b->padded_bases; v.off = b->off; v.len = b->len;
     v.seq2b = b->seq2b; v.qual = b->qual; v.nmask = b->nmask;
-    return v;
+    if (!b->seq2b && b->ascii && b->padded_bases) {            // device-resident text: pack into scratch
+        const size_t words = (size_t)(b->padded_bases >> 4);
+        FL_CUDA(c, c->sc_pack_seq.reserve(words + 4, 0, c->stream));
+        if (want_nmask) FL_CUDA(c, c->sc_pack_nmask.reserve((words >> 1) + 4, 0, c->stream));
+        FL_TRY(fl_pack_ascii_device(c, reinterpret_cast<const uint8_t *>(b->ascii), b->padded_bases, c->sc_pack_seq.p,
+                                    want_nmask ? c->sc_pack_nmask.p : nullptr, c->stream));
+        v.seq2b = c->sc_pack_seq.p;
+        v.nmask = want_nmask ? c->sc_pack_nmask.p : nullptr;
+    }
+    *out = v;
+    return FL_OK;
 }
 
 extern "C" int fl_kmers_add_batch(fl_ctx *c, const fl_batch *h, int multi) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_TRY(check_batch(c, h));
     if (h->n == 0) return FL_OK;
     BatchView v{};
@@ -306,9 +374,11 @@ extern "C" int fl_kmers_add_batch(fl_ctx *c, const fl_batch *h, int multi) {
 }
 
 extern "C" int fl_kmers_add_batch_device(fl_ctx *c, const fl_batch *d, int multi) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_TRY(check_batch(c, d));
-    return fl_kmers_add_view(c, view_of_device_batch(d), multi);
+    BatchView v{};
+    FL_TRY(view_of_device_batch(c, d, true, &v));
+    return fl_kmers_add_view(c, v, multi);
 }
 
 __global__ void k_sum_len(const int32_t *len, uint32_t n, unsigned long long *out) {
@@ -322,7 +392,7 @@ __global__ void k_sum_len(const int32_t *len, uint32_t n, unsigned long long *ou
 #define FL_SCALAR_TOTAL_BASES 16   // slot in d_scalars accumulating the lengths of device batches
 
 extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_TRY(check_batch(c, h));
     if (h->n == 0) return FL_OK;
     if (c->kmers_count_stale || c->multi_pending) FL_TRY(fl_kmers_recount(c));
@@ -345,10 +415,17 @@ extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
 }
 
 extern "C" int fl_reads_push_device(fl_ctx *c, const fl_batch *d) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_TRY(check_batch(c, d));
     if (d->n == 0) return FL_OK;
-    FL_TRY(fl_score_view(c, view_of_device_batch(d)));
+    if (c->kmers_count_stale || c->multi_pending) FL_TRY(fl_kmers_recount(c));
+    BatchView v{};
+    {
+        fl_batch d2 = *d;
+        if (c->n_kmers == 0) d2.ascii = nullptr;                 // Phred mode never reads the bases (read.cpp:35-39)
+        FL_TRY(view_of_device_batch(c, &d2, false, &v));
+    }
+    FL_TRY(fl_score_view(c, v));
     k_sum_len<<<c->sm_count, 256, 0, c->stream>>>(d->len, d->n, c->d_scalars + FL_SCALAR_TOTAL_BASES);
     c->launches++;
     FL_CUDA(c, cudaGetLastError());
@@ -356,7 +433,7 @@ extern "C" int fl_reads_push_device(fl_ctx *c, const fl_batch *d) {
 }
 
 extern "C" int fl_reads_reset(fl_ctx *c) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     FL_CUDA(c, cudaMemsetAsync(c->d_scalars + FL_SCALAR_TOTAL_BASES, 0, sizeof(unsigned long long), c->stream));
     c->n_reads = 0;
     c->n_rows = 0;
@@ -374,7 +451,7 @@ static int device_total_bases(fl_ctx *c, int64_t *out) {
 }
 
 extern "C" int fl_reads_count(fl_ctx *c, uint64_t *n_reads, uint64_t *n_rows, int64_t *total_bases) {
-    if (!c) return FL_EINVAL;
+    FL_ENTER(c);
     if (n_reads) *n_reads = c->n_reads;
     if (n_rows) *n_rows = c->n_rows;
     if (total_bases) FL_TRY(device_total_bases(c, total_bases));
@@ -398,6 +475,7 @@ static double host_length_score(int length) {              // read.cpp:241-244
 
 extern "C" int fl_results_reads(fl_ctx *c, const fl_read_results *o) {
     if (!c || !o) return FL_EINVAL;
+    FL_ENTER(c);
     const size_t n = c->n_reads;
     std::vector<int32_t> len_tmp;
     int32_t *len_host = o->length;
@@ -419,6 +497,7 @@ extern "C" int fl_results_reads(fl_ctx *c, const fl_read_results *o) {
 
 extern "C" int fl_results_rows(fl_ctx *c, const fl_row_results *o) {
     if (!c || !o) return FL_EINVAL;
+    FL_ENTER(c);
     const size_t n = c->n_rows;
     std::vector<int32_t> s_tmp, e_tmp;
     int32_t *s_host = o->start, *e_host = o->end;
@@ -451,6 +530,7 @@ extern "C" int fl_results_rows(fl_ctx *c, const fl_row_results *o) {
 
 extern "C" int fl_results_pass_dev(fl_ctx *c, void **dev_passed_final, uint64_t *n_rows) {
     if (!c || !dev_passed_final) return FL_EINVAL;
+    FL_ENTER(c);
     *dev_passed_final = c->finalized ? (void *)c->w_pfinal.p : (void *)c->w_passed.p;
     if (n_rows) *n_rows = c->n_rows;
     return FL_OK;
@@ -458,6 +538,7 @@ extern "C" int fl_results_pass_dev(fl_ctx *c, void **dev_passed_final, uint64_t 
 
 extern "C" int fl_results_pass(fl_ctx *c, uint8_t *host_out, uint64_t cap, uint64_t *n_rows) {
     if (!c || (!host_out && cap)) return FL_EINVAL;
+    FL_ENTER(c);
     if (n_rows) *n_rows = c->n_rows;
     size_t n = c->n_rows < cap ? c->n_rows : cap;
     if (n) FL_CUDA(c, cudaMemcpyAsync(host_out, c->finalized ? c->w_pfinal.p : c->w_passed.p, n, cudaMemcpyDeviceToHost, c->stream));
@@ -465,164 +546,3 @@ extern "C" int fl_results_pass(fl_ctx *c, uint8_t *host_out, uint64_t cap, uint6
     return FL_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// synthetic workloads: integer-only, counter based -> identical on host and device
-// ---------------------------------------------------------------------------------------------
-__host__ __device__ static inline unsigned long long fl_hash64(unsigned long long seed, unsigned long long a,
-                                                               unsigned long long b) {
-    unsigned long long x = seed + a * 0x9E3779B97F4A7C15ull + b * 0xD6E8FEB86659FD93ull;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    return x;
-}
-
-__host__ __device__ static inline uint8_t synth_qchar(unsigned long long seed, unsigned long long read, unsigned long long pos,
-                                                      int qbar) {
-    unsigned long long h = fl_hash64(seed, read, pos);
-    int s = (int)(h & 0xFF) + (int)((h >> 8) & 0xFF) + (int)((h >> 16) & 0xFF) + (int)((h >> 24) & 0xFF);   // ~N(510, 147.8^2)
-    int z = ((s - 510) * 111 + 2048) >> 12;                                                                  // ~N(0, 4^2), integer only
-    int q = qbar + z;
-    q = q < 1 ? 1 : (q > 50 ? 50 : q);
-    return (uint8_t)(q + 33);
-}
-
-__global__ void k_synth_qual(unsigned long long seed, uint32_t n, const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
-                             const uint8_t *__restrict__ qbar, unsigned long long read_base, uint8_t *__restrict__ qual) {
-    // one warp per read, lanes stride over 16-byte groups
-    const unsigned lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t r = warp; r < n; r += n_warps) {
-        const int L = len[r];
-        const int qb = qbar[r];
-        uint8_t *q = qual + off[r];
-        const int groups = (L + 15) >> 4;
-        for (int g = lane; g < groups; g += 32) {
-            uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                int pos = g * 16 + i;
-                uint8_t ch = pos < L ? synth_qchar(seed, read_base + r, (unsigned long long)pos, qb) : 0;
-                w[i >> 2] |= (uint32_t)ch << (8 * (i & 3));
-            }
-            reinterpret_cast<uint4 *>(q)[g] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-}
-
-extern "C" int fl_synth_qual_device(fl_ctx *c, uint64_t seed, uint32_t n, const uint64_t *dev_off, const int32_t *dev_len,
-                                    const uint8_t *dev_qbar, uint64_t read_index_base, uint8_t *dev_qual) {
-    if (!c) return FL_EINVAL;
-    if (n == 0) return FL_OK;
-    k_synth_qual<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, n, dev_off, dev_len, dev_qbar, read_index_base, dev_qual);
-    FL_CUDA(c, cudaGetLastError());
-    return FL_OK;
-}
-
-extern "C" void fl_synth_qual_host(uint64_t seed, uint32_t n, const uint64_t *off, const int32_t *len, const uint8_t *qbar,
-                                   uint64_t read_index_base, uint8_t *qual) {
-    for (uint32_t r = 0; r < n; ++r)
-        for (int pos = 0; pos < len[r]; ++pos)
-            qual[off[r] + pos] = synth_qchar(seed, read_index_base + r, (unsigned long long)pos, qbar[r]);
-}
-
-#define FL_SYNTH_GENOME_STREAM 0x47454E4F4D45ull
-
-__host__ __device__ static inline uint32_t synth_genome_word(unsigned long long seed, unsigned long long w) {
-    return (uint32_t)(fl_hash64(seed, FL_SYNTH_GENOME_STREAM, w) >> 16);
-}
-
-__global__ void k_synth_genome(unsigned long long seed, unsigned long long n_bases, uint32_t *__restrict__ out) {
-    const unsigned long long words = (n_bases + 15) >> 4;
-    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < words;
-         w += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t v = synth_genome_word(seed, w);
-        unsigned long long rem = n_bases - (w << 4);
-        if (rem < 16) v &= ~(0xFFFFFFFFu >> (2 * rem));     // bases beyond the end stay 0
-        out[w] = v;
-    }
-}
-
-extern "C" int fl_synth_genome_device(fl_ctx *c, uint64_t seed, uint64_t n_bases, uint32_t *dev_seq2b) {
-    if (!c) return FL_EINVAL;
-    k_synth_genome<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, n_bases, dev_seq2b);
-    FL_CUDA(c, cudaGetLastError());
-    return FL_OK;
-}
-
-extern "C" void fl_synth_genome_host(uint64_t seed, uint64_t n_bases, uint32_t *seq2b) {
-    const uint64_t words = (n_bases + 15) >> 4;
-    for (uint64_t w = 0; w < words; ++w) {
-        uint32_t v = synth_genome_word(seed, w);
-        uint64_t rem = n_bases - (w << 4);
-        if (rem < 16) v &= ~(0xFFFFFFFFu >> (2 * rem));
-        seq2b[w] = v;
-    }
-}
-
-__host__ __device__ static inline uint32_t genome_code(const uint32_t *g, unsigned long long pos) {
-    return (g[pos >> 4] >> (30 - 2 * (pos & 15))) & 3u;
-}
-
-__host__ __device__ static inline uint32_t synth_read_code(unsigned long long seed, const uint32_t *genome, unsigned long long start,
-                                                           int len, int strand, uint32_t err_ppm, int junk_pos, int junk_len,
-                                                           unsigned long long read, int i) {
-    unsigned long long h = fl_hash64(seed, read, (unsigned long long)i);
-    if (junk_len > 0 && i >= junk_pos && i < junk_pos + junk_len) return (uint32_t)(h >> 40) & 3u;
-    uint32_t code = strand ? 3u - genome_code(genome, start + (unsigned long long)(len - 1 - i)) : genome_code(genome, start + (unsigned long long)i);
-    unsigned long long thr = ((unsigned long long)err_ppm << 20) / 1000000ull;
-    if (((h >> 8) & 0xFFFFFull) < thr) code = (code + 1u + (uint32_t)((h >> 32) % 3ull)) & 3u;
-    return code;
-}
-
-__global__ void k_synth_reads(unsigned long long seed, const uint32_t *__restrict__ genome, fl_synth_reads d,
-                              unsigned long long read_base, uint32_t *__restrict__ out) {
-    const unsigned lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t r = warp; r < d.n; r += n_warps) {
-        const int L = d.len[r];
-        const unsigned long long st = d.start[r];
-        const int strand = d.strand[r];
-        const uint32_t err = d.err_ppm[r];
-        const int jp = d.junk_pos[r], jl = d.junk_len[r];
-        uint32_t *o = out + (d.off[r] >> 4);
-        const int words = L > 0 ? (int)((((unsigned)L + 63u) & ~63u) >> 4) : 0;
-        for (int w = lane; w < words; w += 32) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                int i = w * 16 + k;
-                if (i < L) v |= synth_read_code(seed, genome, st, L, strand, err, jp, jl, read_base + r, i) << (30 - 2 * k);
-            }
-            o[w] = v;
-        }
-    }
-}
-
-extern "C" int fl_synth_reads_device(fl_ctx *c, uint64_t seed, const uint32_t *dev_genome2b, const fl_synth_reads *dev_desc,
-                                     uint64_t read_index_base, uint32_t *dev_seq2b) {
-    if (!c || !dev_desc) return FL_EINVAL;
-    if (dev_desc->n == 0) return FL_OK;
-    k_synth_reads<<<c->sm_count * 8, 256, 0, c->stream>>>(seed, dev_genome2b, *dev_desc, read_index_base, dev_seq2b);
-    FL_CUDA(c, cudaGetLastError());
-    return FL_OK;
-}
-
-extern "C" void fl_synth_reads_host(uint64_t seed, const uint32_t *genome2b, const fl_synth_reads *d, uint64_t read_index_base,
-                                    uint32_t *seq2b) {
-    for (uint32_t r = 0; r < d->n; ++r) {
-        const int L = d->len[r];
-        uint32_t *o = seq2b + (d->off[r] >> 4);
-        const int words = (int)(fl_padded_len(L) >> 4);
-        for (int w = 0; w < words; ++w) {
-            uint32_t v = 0;
-            for (int k = 0; k < 16; ++k) {
-                int i = w * 16 + k;
-                if (i < L)
-                    v |= synth_read_code(seed, genome2b, d->start[r], L, d->strand[r], d->err_ppm[r], d->junk_pos[r], d->junk_len[r],
-                                         read_index_base + r, i) << (30 - 2 * k);
-            }
-            o[w] = v;
-        }
-    }
-}

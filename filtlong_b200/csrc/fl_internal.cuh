@@ -14,6 +14,10 @@
 #define FL_BLOOM_BITS 1917295480ull   // bloom_filter.h:108-160 with kmers.cpp:32-34's parameters
 #define FL_BLOOM_K 13
 #define FL_ORDER_BUCKETS 1024
+#define FL_COMM_MAX_RANKS 64
+#define FL_SELECT_DIGIT_BITS 13           // the cut-off key is found 13 bits at a time: 5 levels for a 64-bit key
+#define FL_SELECT_BINS (1 << FL_SELECT_DIGIT_BITS)
+#define FL_COMM_SCRATCH_BYTES (FL_SELECT_BINS * 8 + 4096 * 8)
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing: CUDA failures become FL_ECUDA + message, never exceptions
@@ -25,6 +29,13 @@
             (ctx)->set_error(std::string(#call) + ": " + cudaGetErrorString(e__));             \
             return FL_ECUDA;                                                                   \
         }                                                                                      \
+    } while (0)
+
+// every public entry point runs on its context's device (one process may hold one context per GPU)
+#define FL_ENTER(c)                                   \
+    do {                                              \
+        if (!(c)) return FL_EINVAL;                   \
+        FL_CUDA((c), cudaSetDevice((c)->device));     \
     } while (0)
 
 #define FL_TRY(expr)                \
@@ -75,6 +86,7 @@ struct BatchView {
     const uint32_t *seq2b;
     const uint8_t *qual;
     const uint32_t *nmask;
+    const uint8_t *ascii;
 };
 
 // State of the weighted radix select, lives in device memory (one instance per context).
@@ -130,6 +142,7 @@ struct fl_ctx {
     int phred_mode = 1;                     // 1: k_phred_sum + k_phred_win (default); 0: work-item kernels (FL_PHRED_MODE)
     int phred_occupancy = 4;                // blocks per SM launched for k_phred_sum / k_phred_win (FL_PHRED_OCC)
     int lut_window = -1;
+    bool phred_attr_set = false, phred_items_attr_set = false;   // cudaFuncSetAttribute is per DEVICE: kept per context
 
     // ---- staging for host batches ----
     // two slots: the host->device copy of batch i+1 (copy_stream) overlaps the kernels of batch i
@@ -137,7 +150,7 @@ struct fl_ctx {
         DevVec<uint64_t> off;
         DevVec<int32_t> len;
         DevVec<uint32_t> seq, nmask;
-        DevVec<uint8_t> qual;
+        DevVec<uint8_t> qual, ascii;
         cudaEvent_t consumed = nullptr;   // recorded on the compute stream after the last kernel that reads this slot
         bool in_use = false;
     } stg[2];
@@ -146,6 +159,7 @@ struct fl_ctx {
     cudaEvent_t ev_copied = nullptr;
 
     // ---- per-batch scratch ----
+    DevVec<uint32_t> sc_pack_seq, sc_pack_nmask;   // 2-bit codes / non-ACGT mask packed on the device from an ASCII DEVICE batch
     DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer
     DevVec<uint32_t> sc_order;       // rows in descending-length bucket order
     DevVec<unsigned long long> sc_u64a, sc_u64b, sc_u64c;
@@ -177,6 +191,13 @@ struct fl_ctx {
     double *d_norm = nullptr;            // sums4, min1, max1, sq1 (+ padding)
     unsigned long long *d_hist = nullptr;  // 256 bins + tie/keeping scalars
     DevVec<double> sc_f64;
+
+    // ---- sharded read set: one NCCL communicator per context (fl_comm.cu) ----
+    void *comm = nullptr;                // ncclComm_t
+    int comm_rank = 0, comm_nranks = 1;
+    unsigned char *d_comm = nullptr;     // FL_COMM_SCRATCH_BYTES of send / receive buffers for the collectives of fl_finalize
+    uint64_t collectives = 0;            // NCCL calls issued so far
+    bool select_attr_set = false;
 
     // ---- optional per-kernel timing (fl_ctx_enable_timing) ----
     bool timing = false;
@@ -217,6 +238,10 @@ int fl_order_by_length(fl_ctx *ctx, const int32_t *len, size_t n, uint32_t *orde
 // same with caller-computed bucket keys in [0, FL_ORDER_BUCKETS): highest key first
 int fl_order_by_key(fl_ctx *ctx, const uint32_t *key, size_t n, uint32_t *order);
 
+// ---- implemented in fl_api.cu ----
+// text -> 2-bit codes (+ non-ACGT mask when nmask != null), kmers.cpp:176-196 on the device
+int fl_pack_ascii_device(fl_ctx *ctx, const uint8_t *ascii, uint64_t padded_bases, uint32_t *seq2b, uint32_t *nmask, cudaStream_t s);
+
 // ---- implemented in fl_kmers.cu ----
 int fl_kmers_ensure_bitmap(fl_ctx *ctx);
 int fl_kmers_add_view(fl_ctx *ctx, const BatchView &b, int multi);
@@ -229,6 +254,10 @@ int fl_reserve_rows(fl_ctx *ctx, size_t n_total);
 
 // ---- implemented in fl_phred.cu ----
 int fl_score_phred(fl_ctx *ctx, const BatchView &b);
+
+// ---- implemented in fl_comm.cu (no-ops / plain copies on a context without a communicator) ----
+int fl_comm_allgather(fl_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int fl_comm_allreduce_u64(fl_ctx *ctx, unsigned long long *buf, size_t n);
 
 // ---- implemented in fl_select.cu ----
 int fl_norm_select_free(fl_ctx *ctx);

@@ -236,16 +236,34 @@ int fl_kmers_ensure_bitmap(fl_ctx *ctx) {
     return FL_OK;
 }
 
-static int ensure_multi_state(fl_ctx *ctx) {
-    if (ctx->d_tfirst) return FL_OK;
+static void free_multi_state(fl_ctx *ctx) {
     for (int i = 0; i < 4; ++i) {
-        FL_CUDA(ctx, cudaMalloc(&ctx->d_seen[i], (size_t)1 << 29));
-        FL_CUDA(ctx, cudaMemsetAsync(ctx->d_seen[i], 0, (size_t)1 << 29, ctx->stream));
+        if (ctx->d_seen[i]) cudaFree(ctx->d_seen[i]);
+        ctx->d_seen[i] = nullptr;
     }
-    FL_CUDA(ctx, cudaMalloc(&ctx->d_tfirst, ((size_t)1 << 32) * sizeof(unsigned long long)));
-    FL_CUDA(ctx, cudaMemsetAsync(ctx->d_tfirst, 0xFF, ((size_t)1 << 32) * sizeof(unsigned long long), ctx->stream));
-    FL_CUDA(ctx, cudaMalloc(&ctx->d_bittime, (size_t)FL_BLOOM_BITS * sizeof(unsigned long long)));
-    FL_CUDA(ctx, cudaMemsetAsync(ctx->d_bittime, 0xFF, (size_t)FL_BLOOM_BITS * sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_tfirst) cudaFree(ctx->d_tfirst);
+    if (ctx->d_bittime) cudaFree(ctx->d_bittime);
+    ctx->d_tfirst = nullptr;
+    ctx->d_bittime = nullptr;
+}
+
+// all or nothing: a partial allocation failure frees what was taken, so a later call starts clean
+static int ensure_multi_state(fl_ctx *ctx) {
+    if (ctx->d_tfirst && ctx->d_bittime && ctx->d_seen[0] && ctx->d_seen[1] && ctx->d_seen[2] && ctx->d_seen[3]) return FL_OK;
+    free_multi_state(ctx);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaMalloc(&ctx->d_seen[i], (size_t)1 << 29);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tfirst, ((size_t)1 << 32) * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_bittime, (size_t)FL_BLOOM_BITS * sizeof(unsigned long long));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaMemsetAsync(ctx->d_seen[i], 0, (size_t)1 << 29, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_tfirst, 0xFF, ((size_t)1 << 32) * sizeof(unsigned long long), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_bittime, 0xFF, (size_t)FL_BLOOM_BITS * sizeof(unsigned long long), ctx->stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        free_multi_state(ctx);
+        ctx->set_error(std::string("multiple-copy build state (49 GiB): ") + cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? FL_ENOMEM : FL_ECUDA;
+    }
     return FL_OK;
 }
 
@@ -337,7 +355,7 @@ int fl_kmers_recount(fl_ctx *ctx) {
 
 // ---- C ABI ------------------------------------------------------------------------------------
 extern "C" int fl_kmers_finalize(fl_ctx *ctx, uint64_t *n_kmers_out) {
-    if (!ctx) return FL_EINVAL;
+    FL_ENTER(ctx);
     if (ctx->kmers_count_stale || ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
     if (n_kmers_out) *n_kmers_out = ctx->n_kmers;
     return FL_OK;
@@ -345,6 +363,7 @@ extern "C" int fl_kmers_finalize(fl_ctx *ctx, uint64_t *n_kmers_out) {
 
 extern "C" int fl_kmers_contains(fl_ctx *ctx, const uint32_t *kmers, uint32_t n, uint8_t *out) {
     if (!ctx || (!kmers && n) || (!out && n)) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(fl_kmers_finalize(ctx, nullptr));
     if (n == 0) return FL_OK;
     if (!ctx->d_bitmap) { memset(out, 0, n); return FL_OK; }
@@ -360,7 +379,7 @@ extern "C" int fl_kmers_contains(fl_ctx *ctx, const uint32_t *kmers, uint32_t n,
 }
 
 extern "C" int fl_kmers_export(fl_ctx *ctx, uint32_t *out, uint64_t cap, uint64_t *n_out) {
-    if (!ctx) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(fl_kmers_finalize(ctx, nullptr));
     if (n_out) *n_out = ctx->n_kmers;
     if (!ctx->d_bitmap || !out || cap == 0) return FL_OK;
@@ -381,6 +400,7 @@ extern "C" int fl_kmers_export(fl_ctx *ctx, uint32_t *out, uint64_t cap, uint64_
 
 extern "C" int fl_kmers_bitmap_dev(fl_ctx *ctx, void **dev_ptr, uint64_t *n_bytes) {
     if (!ctx || !dev_ptr) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(fl_kmers_ensure_bitmap(ctx));
     *dev_ptr = ctx->d_bitmap;
     if (n_bytes) *n_bytes = (uint64_t)1 << 29;
@@ -388,22 +408,15 @@ extern "C" int fl_kmers_bitmap_dev(fl_ctx *ctx, void **dev_ptr, uint64_t *n_byte
 }
 
 extern "C" int fl_kmers_bitmap_changed(fl_ctx *ctx) {
-    if (!ctx) return FL_EINVAL;
+    FL_ENTER(ctx);
     ctx->kmers_count_stale = true;
     return FL_OK;
 }
 
 extern "C" int fl_kmers_release_build_state(fl_ctx *ctx) {
-    if (!ctx) return FL_EINVAL;
+    FL_ENTER(ctx);
     if (ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
     FL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < 4; ++i) {
-        if (ctx->d_seen[i]) cudaFree(ctx->d_seen[i]);
-        ctx->d_seen[i] = nullptr;
-    }
-    if (ctx->d_tfirst) cudaFree(ctx->d_tfirst);
-    if (ctx->d_bittime) cudaFree(ctx->d_bittime);
-    ctx->d_tfirst = nullptr;
-    ctx->d_bittime = nullptr;
+    free_multi_state(ctx);
     return FL_OK;
 }

@@ -922,15 +922,14 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         FL_CUDA(ctx, cudaMemsetAsync(a.fallback, 0, sizeof(uint32_t), st));
         a.work = ctx->d_scalars + 24;
         FL_CUDA(ctx, cudaMemsetAsync(a.work, 0, 2 * sizeof(unsigned long long), st));
-        static bool tile_attr_set = false;
-        if (!tile_attr_set) {
+        if (!ctx->phred_attr_set) {
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_first, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
-            tile_attr_set = true;
+            ctx->phred_attr_set = true;
         }
         {
             unsigned hb = fl_blocks(n, PH_THREADS);
@@ -998,11 +997,10 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     a.item_start = ctx->sc_u64a.p; a.order = ctx->sc_order.p; a.items = items; a.n_items = n_items;
     a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n_items; a.it_c = ctx->sc_f64.p + 2 * n_items;
     a.fallback = fallback;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->phred_items_attr_set) {
         FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_items, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
         FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
-        attr_set = true;
+        ctx->phred_items_attr_set = true;
     }
     unsigned blocks = fl_blocks(n_items, PH_THREADS);
     const unsigned max_blocks = (unsigned)ctx->sm_count * 3;

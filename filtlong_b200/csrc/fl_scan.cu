@@ -38,8 +38,8 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const unsigned long long *__restrict__ in,
-                                                            unsigned long long *__restrict__ out, size_t n,
+// in == out is allowed (callers scan in place), so neither pointer is __restrict__
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const unsigned long long *in, unsigned long long *out, size_t n,
                                                             unsigned long long *__restrict__ tile_sums) {
     __shared__ unsigned long long total;
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;

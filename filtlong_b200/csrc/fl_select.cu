@@ -325,6 +325,182 @@ __global__ void __launch_bounds__(256) k_select_cut(CutArgs a) {
     if ((threadIdx.x & 31) == 0 && kept) atomicAdd(a.keeping, kept);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fl_finalize: the same block with its exchanges behind the C ABI (fl_comm.cu). Scratch in ctx->d_comm:
+// ---------------------------------------------------------------------------------------------
+struct CommScratch {
+    unsigned long long hist[FL_SELECT_BINS];       // base-weighted histogram of one 13-bit digit (all-reduced)
+    double stats_send[8];                          // n, sum(mean_q), passed bases, row bases, min, max, input bases, -
+    double stats_recv[8 * FL_COMM_MAX_RANKS];
+    double sq_send[8];
+    double sq_recv[8 * FL_COMM_MAX_RANKS];         // one double per rank (8-byte stride)
+    unsigned long long tie_send[8];
+    unsigned long long tie_recv[FL_COMM_MAX_RANKS];
+    unsigned long long keeping[8];
+    long long total_bases[8];                      // [0] global input bases (main.cpp:89 summed over the shards)
+};
+static_assert(sizeof(CommScratch) <= FL_COMM_SCRATCH_BYTES, "scratch block too small");
+
+__global__ void k_stats_send(const double *sums4, const double *min1, const double *max1, const unsigned long long *dev_bases,
+                             long long host_bases, double *send) {
+    if (threadIdx.x || blockIdx.x) return;
+    send[0] = sums4[0]; send[1] = sums4[1]; send[2] = sums4[2]; send[3] = sums4[3];
+    send[4] = *min1; send[5] = *max1;
+    send[6] = (double)(host_bases + (dev_bases ? (long long)*dev_bases : 0ll));     // < 2^53: exact
+    send[7] = 0.0;
+}
+
+// combine the ranks' partials in rank order: every rank computes the same bits, whatever NCCL did inside
+__global__ void k_stats_combine(const double *recv, int nranks, double *sums4, double *min1, double *max1, long long *total) {
+    if (threadIdx.x || blockIdx.x) return;
+    double a[4] = {0, 0, 0, 0}, mn = 100.0, mx = 0.0, tb = 0.0;                     // main.cpp:170-172
+    for (int r = 0; r < nranks; ++r) {
+        const double *p = recv + 8 * r;
+        for (int k = 0; k < 4; ++k) a[k] += p[k];
+        if (p[4] < mn) mn = p[4];
+        if (p[5] > mx) mx = p[5];
+        tb += p[6];
+    }
+    for (int k = 0; k < 4; ++k) sums4[k] = a[k];
+    *min1 = mn;
+    *max1 = mx;
+    *total = (long long)tb;
+}
+
+__global__ void k_sq_combine(const double *recv, int nranks, double *sq1) {
+    if (threadIdx.x || blockIdx.x) return;
+    double a = 0.0;
+    for (int r = 0; r < nranks; ++r) a += recv[r];
+    *sq1 = a;
+}
+
+__global__ void k_select_begin_dev(SelectState *st, const double *sums4, const long long *total, fl_params p) {
+    if (threadIdx.x || blockIdx.x) return;
+    SelectState s{};
+    const long long total_bases = *total;
+    const int any = p.target_bases_set || p.keep_percent_set;
+    long long target = 0;
+    if (any) {
+        target = p.target_bases_set ? (long long)p.target_bases : 0x7FFFFFFFFFFFFFFFll;             // main.cpp:229-232
+        if (p.keep_percent_set) {
+            const long long keep_target = (long long)((p.keep_percent / 100.0) * (double)total_bases);   // main.cpp:235
+            if (keep_target < target) target = keep_target;
+        }
+    }
+    s.target = target;
+    s.total_bases = total_bases;
+    s.passed_bases = (long long)sums4[2];
+    if (!any) s.status = 0;
+    else if (target >= total_bases) s.status = 1;                            // main.cpp:239-240
+    else if (target >= s.passed_bases) s.status = 2;                         // main.cpp:242-243
+    else s.status = 3;
+    s.active = s.status == 3;
+    *st = s;
+}
+
+struct WideHistArgs {
+    size_t n;
+    const unsigned long long *key;
+    const int32_t *start, *end;
+    const uint8_t *passed;
+    const SelectState *st;
+    int shift, width, first;      // digit = (key >> shift) & ((1 << width) - 1); rows must match st->prefix above it
+    unsigned long long *hist;     // [FL_SELECT_BINS], zeroed
+};
+
+__global__ void __launch_bounds__(256) k_select_hist_wide(WideHistArgs a) {
+    extern __shared__ unsigned long long hw[];
+    for (int i = threadIdx.x; i < FL_SELECT_BINS; i += blockDim.x) hw[i] = 0ull;
+    __syncthreads();
+    if (!a.st->active) return;
+    const unsigned long long prefix = a.st->prefix;
+    const unsigned long long dmask = (1ull << a.width) - 1ull;
+    const int up = a.shift + a.width;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) {
+        if (!a.passed[i]) continue;
+        const unsigned long long k = a.key[i];
+        if (!a.first && (k >> up) != prefix) continue;
+        atomicAdd(&hw[(k >> a.shift) & dmask], (unsigned long long)(a.end[i] - a.start[i]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FL_SELECT_BINS; i += blockDim.x)
+        if (hw[i]) atomicAdd(&a.hist[i], hw[i]);
+}
+
+// one block of 1024 threads, 8 bins each: first non-empty bin whose inclusive prefix reaches the target
+__global__ void __launch_bounds__(1024) k_select_pick_wide(SelectState *st, const unsigned long long *hist, int width, int last) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ int s_pick, s_lastne;
+    __shared__ unsigned long long s_before_pick;
+    if (!st->active) return;
+    const int nb = 1 << width;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long c[8], s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int d = (int)threadIdx.x * 8 + i;
+        c[i] = d < nb ? hist[d] : 0ull;
+        s += c[i];
+    }
+    unsigned long long incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    if (threadIdx.x == 0) { s_pick = 0x7FFFFFFF; s_lastne = -1; }
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long v = wsum[lane], iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, iv, d);
+            if (lane >= (unsigned)d) iv += t;
+        }
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    const unsigned long long base = st->cum_before, target = (unsigned long long)st->target;
+    unsigned long long cum = base + wsum[wid] + (incl - s);
+    int my_pick = 0x7FFFFFFF, my_last = -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int d = (int)threadIdx.x * 8 + i;
+        if (c[i]) {
+            my_last = d;
+            if (my_pick == 0x7FFFFFFF && cum + c[i] >= target) my_pick = d;
+        }
+        cum += c[i];
+    }
+    if (my_pick != 0x7FFFFFFF) atomicMin(&s_pick, my_pick);
+    if (my_last >= 0) atomicMax(&s_lastne, my_last);
+    __syncthreads();
+    // the owner of the picked (or, if none reaches the target, the last non-empty) bin publishes its prefix
+    int pick = s_pick != 0x7FFFFFFF ? s_pick : (s_lastne < 0 ? 0 : s_lastne);
+    cum = base + wsum[wid] + (incl - s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int d = (int)threadIdx.x * 8 + i;
+        if (d == pick) { s_before_pick = cum; }
+        cum += c[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->cum_before = s_before_pick;
+        st->prefix = (st->prefix << width) | (unsigned long long)pick;
+        if (last) {
+            st->tie_key = st->prefix;
+            st->tie_base = target > st->cum_before ? target - st->cum_before : 0ull;
+        }
+    }
+}
+
+__global__ void k_copy_u64(const unsigned long long *src, unsigned long long *dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
+
 }  // namespace
 
 static RowsView rows_view(fl_ctx *c) {
@@ -358,6 +534,7 @@ static int red_blocks(fl_ctx *c) {
 
 extern "C" int fl_norm_partial1(fl_ctx *ctx, double *dev_sums4, double *dev_min1, double *dev_max1) {
     if (!ctx || !dev_sums4 || !dev_min1 || !dev_max1) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(ensure_final_buffers(ctx));
     int nb = red_blocks(ctx);
     k_norm_p1<<<nb, RED_THREADS, 0, ctx->stream>>>(rows_view(ctx), ctx->sc_f64.p);
@@ -369,6 +546,7 @@ extern "C" int fl_norm_partial1(fl_ctx *ctx, double *dev_sums4, double *dev_min1
 
 extern "C" int fl_norm_partial2(fl_ctx *ctx, const double *dev_sums4, const double *, const double *, double *dev_sq1) {
     if (!ctx || !dev_sums4 || !dev_sq1) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(ensure_final_buffers(ctx));
     int nb = red_blocks(ctx);
     k_norm_p2<<<nb, RED_THREADS, 0, ctx->stream>>>(rows_view(ctx), dev_sums4, ctx->sc_f64.p);
@@ -381,6 +559,7 @@ extern "C" int fl_norm_partial2(fl_ctx *ctx, const double *dev_sums4, const doub
 extern "C" int fl_norm_apply(fl_ctx *ctx, const double *dev_sums4, const double *dev_min1, const double *dev_max1,
                              const double *dev_sq1) {
     if (!ctx || !dev_sums4 || !dev_min1 || !dev_max1 || !dev_sq1) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(ensure_final_buffers(ctx));
     if (ctx->n_rows == 0) return FL_OK;
     ApplyArgs a{};
@@ -408,6 +587,7 @@ static long long compute_target(const fl_params &p, long long total_bases) {
 
 extern "C" int fl_select_begin(fl_ctx *ctx, int64_t total_bases_global, const double *dev_sums4) {
     if (!ctx || !dev_sums4) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_TRY(ensure_final_buffers(ctx));
     const int any = ctx->p.target_bases_set || ctx->p.keep_percent_set;
     long long target = any ? compute_target(ctx->p, total_bases_global) : 0;
@@ -419,6 +599,7 @@ extern "C" int fl_select_begin(fl_ctx *ctx, int64_t total_bases_global, const do
 
 extern "C" int fl_select_hist(fl_ctx *ctx, int level, uint64_t *dev_hist256) {
     if (!ctx || !dev_hist256 || level < 0 || level > 7) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_CUDA(ctx, cudaMemsetAsync(dev_hist256, 0, 256 * sizeof(uint64_t), ctx->stream));
     if (ctx->n_rows == 0) return FL_OK;
     HistArgs a{};
@@ -435,6 +616,7 @@ extern "C" int fl_select_hist(fl_ctx *ctx, int level, uint64_t *dev_hist256) {
 
 extern "C" int fl_select_pick(fl_ctx *ctx, int level, const uint64_t *dev_hist256) {
     if (!ctx || !dev_hist256 || level < 0 || level > 7) return FL_EINVAL;
+    FL_ENTER(ctx);
     k_select_pick<<<1, 1, 0, ctx->stream>>>(ctx->d_sel, reinterpret_cast<const unsigned long long *>(dev_hist256), level);
     ctx->launches++;
     FL_CUDA(ctx, cudaGetLastError());
@@ -443,6 +625,7 @@ extern "C" int fl_select_pick(fl_ctx *ctx, int level, const uint64_t *dev_hist25
 
 extern "C" int fl_select_tie_local(fl_ctx *ctx, uint64_t *dev_tie_per_rank, int rank, int nranks) {
     if (!ctx || !dev_tie_per_rank || rank < 0 || rank >= nranks) return FL_EINVAL;
+    FL_ENTER(ctx);
     size_t n = ctx->n_rows;
     FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, ctx->stream));
     FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, ctx->stream));
@@ -465,6 +648,7 @@ extern "C" int fl_select_tie_local(fl_ctx *ctx, uint64_t *dev_tie_per_rank, int 
 
 extern "C" int fl_select_apply(fl_ctx *ctx, const uint64_t *dev_tie_per_rank, int rank, uint64_t *dev_keeping1) {
     if (!ctx || !dev_tie_per_rank || !dev_keeping1) return FL_EINVAL;
+    FL_ENTER(ctx);
     FL_CUDA(ctx, cudaMemsetAsync(dev_keeping1, 0, sizeof(uint64_t), ctx->stream));
     if (ctx->n_rows) {
         CutArgs a{};
@@ -488,6 +672,7 @@ extern "C" int fl_select_summary(fl_ctx *ctx, const double *dev_sums4, const dou
                                  const double *dev_sq1, const uint64_t *dev_keeping1, int64_t total_bases_global,
                                  fl_summary *out) {
     if (!ctx || !out) return FL_EINVAL;
+    FL_ENTER(ctx);
     double h[8] = {0};
     unsigned long long keeping = 0;
     SelectState st{};
@@ -513,27 +698,86 @@ extern "C" int fl_select_summary(fl_ctx *ctx, const double *dev_sums4, const dou
 }
 
 extern "C" int fl_finalize(fl_ctx *ctx, int64_t total_bases, fl_summary *out) {
-    if (!ctx) return FL_EINVAL;
-    if (total_bases < 0) FL_TRY(fl_reads_count(ctx, nullptr, nullptr, &total_bases));
+    FL_ENTER(ctx);
     FL_TRY(ensure_final_buffers(ctx));
-    double *sums = ctx->d_norm, *mn = ctx->d_norm + 4, *mx = ctx->d_norm + 5, *sq = ctx->d_norm + 6;
-    uint64_t *hist = reinterpret_cast<uint64_t *>(ctx->d_hist);
-    uint64_t *tie = hist + 256, *keeping = hist + 257;
-    FL_TRY(fl_norm_partial1(ctx, sums, mn, mx));
-    FL_TRY(fl_norm_partial2(ctx, sums, mn, mx, sq));
-    FL_TRY(fl_norm_apply(ctx, sums, mn, mx, sq));
-    FL_TRY(fl_select_begin(ctx, total_bases, sums));
-    if (ctx->p.target_bases_set || ctx->p.keep_percent_set) {
-        for (int level = 0; level < 8; ++level) {
-            FL_TRY(fl_select_hist(ctx, level, hist));
-            FL_TRY(fl_select_pick(ctx, level, hist));
-        }
-        FL_TRY(fl_select_tie_local(ctx, tie, 0, 1));
-    } else {
-        FL_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(uint64_t), ctx->stream));
+    if (ctx->comm_nranks > FL_COMM_MAX_RANKS) { ctx->set_error("fl_finalize: too many ranks"); return FL_ERANGE; }
+    if (!ctx->d_comm) FL_CUDA(ctx, cudaMalloc(&ctx->d_comm, FL_COMM_SCRATCH_BYTES));
+    if (!ctx->select_attr_set) {
+        FL_CUDA(ctx, cudaFuncSetAttribute(k_select_hist_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SELECT_BINS * 8));
+        ctx->select_attr_set = true;
     }
-    FL_TRY(fl_select_apply(ctx, tie, 0, keeping));
-    if (out) FL_TRY(fl_select_summary(ctx, sums, mn, mx, sq, keeping, total_bases, out));
+    cudaStream_t st = ctx->stream;
+    CommScratch *cs = reinterpret_cast<CommScratch *>(ctx->d_comm);
+    double *sums = ctx->d_norm, *mn = ctx->d_norm + 4, *mx = ctx->d_norm + 5, *sq = ctx->d_norm + 6;
+    const int nranks = ctx->comm_nranks, rank = ctx->comm_rank;
+    const size_t n = ctx->n_rows;
+    // ---- statistics (main.cpp:170-196): local partials, one all-gather each, combined in rank order ----
+    FL_TRY(fl_norm_partial1(ctx, sums, mn, mx));
+    {
+        const bool own = total_bases < 0;                 // the context's own count: host pushes + device pushes
+        k_stats_send<<<1, 1, 0, st>>>(sums, mn, mx, own ? ctx->d_scalars + 16 : nullptr, own ? (long long)ctx->total_bases : (long long)total_bases,
+                                      cs->stats_send);
+        ctx->launches++;
+    }
+    FL_TRY(fl_comm_allgather(ctx, cs->stats_send, cs->stats_recv, 8 * sizeof(double)));
+    k_stats_combine<<<1, 1, 0, st>>>(cs->stats_recv, nranks, sums, mn, mx, cs->total_bases);
+    ctx->launches++;
+    FL_TRY(fl_norm_partial2(ctx, sums, mn, mx, cs->sq_send));
+    FL_TRY(fl_comm_allgather(ctx, cs->sq_send, cs->sq_recv, sizeof(double)));
+    k_sq_combine<<<1, 1, 0, st>>>(cs->sq_recv, nranks, sq);
+    ctx->launches++;
+    FL_TRY(fl_norm_apply(ctx, sums, mn, mx, sq));                                   // main.cpp:202-212
+    // ---- target + weighted radix select of the cut-off key (main.cpp:218-257) ----
+    k_select_begin_dev<<<1, 1, 0, st>>>(ctx->d_sel, sums, cs->total_bases, ctx->p);
+    ctx->launches++;
+    const bool any_target = ctx->p.target_bases_set || ctx->p.keep_percent_set;
+    if (any_target) {
+        int done = 0;
+        while (done < 64) {
+            const int width = 64 - done < FL_SELECT_DIGIT_BITS ? 64 - done : FL_SELECT_DIGIT_BITS;
+            const int shift = 64 - done - width;
+            FL_CUDA(ctx, cudaMemsetAsync(cs->hist, 0, sizeof(cs->hist), st));
+            if (n) {
+                WideHistArgs a{};
+                a.n = n; a.key = ctx->w_key.p; a.start = ctx->w_start.p; a.end = ctx->w_end.p; a.passed = ctx->w_passed.p;
+                a.st = ctx->d_sel; a.shift = shift; a.width = width; a.first = done == 0; a.hist = cs->hist;
+                unsigned blocks = fl_blocks(n, 256 * 16);
+                if (blocks > (unsigned)ctx->sm_count * 2) blocks = (unsigned)ctx->sm_count * 2;
+                if (blocks < 1) blocks = 1;
+                k_select_hist_wide<<<blocks, 256, FL_SELECT_BINS * 8, st>>>(a);
+                ctx->launches++;
+            }
+            FL_TRY(fl_comm_allreduce_u64(ctx, cs->hist, (size_t)1 << width));
+            k_select_pick_wide<<<1, 1024, 0, st>>>(ctx->d_sel, cs->hist, width, shift == 0);
+            ctx->launches++;
+            done += width;
+        }
+        // tie class at the cut-off, in (rank, row) order
+        FL_CUDA(ctx, ctx->sc_u64a.reserve(n + 1, 0, st));
+        FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, st));
+        if (n) {
+            TieArgs a{};
+            a.n = n; a.key = ctx->w_key.p; a.start = ctx->w_start.p; a.end = ctx->w_end.p; a.passed = ctx->w_passed.p;
+            a.st = ctx->d_sel; a.tie_len = ctx->sc_u64a.p;
+            unsigned blocks = fl_blocks(n, 256);
+            if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+            k_tie_len<<<blocks, 256, 0, st>>>(a);
+            ctx->launches++;
+        }
+        FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64a.p, ctx->sc_u64b.p, n, cs->tie_send));
+        FL_TRY(fl_comm_allgather(ctx, cs->tie_send, cs->tie_recv, sizeof(unsigned long long)));
+    } else {
+        FL_CUDA(ctx, cudaMemsetAsync(cs->tie_recv, 0, sizeof(cs->tie_recv), st));
+    }
+    FL_TRY(fl_select_apply(ctx, reinterpret_cast<const uint64_t *>(cs->tie_recv), rank, reinterpret_cast<uint64_t *>(cs->keeping)));
+    FL_TRY(fl_comm_allreduce_u64(ctx, cs->keeping, 1));
+    FL_CUDA(ctx, cudaGetLastError());
+    if (out) {
+        long long total = 0;
+        FL_CUDA(ctx, cudaMemcpyAsync(&total, cs->total_bases, sizeof(total), cudaMemcpyDeviceToHost, st));
+        FL_TRY(fl_select_summary(ctx, sums, mn, mx, sq, reinterpret_cast<const uint64_t *>(cs->keeping), -1, out));
+        out->total_bases = total;
+    }
     return FL_OK;
 }
 

@@ -43,7 +43,11 @@ void Kmers::add_read_fastqs(std::vector<std::string> filenames) {
     std::cerr << "Hashing 16-mers from short reads\n";
     int sequence_count = 0;
     for (auto &filename : filenames) sequence_count += add_reference(filename, true);
-    std::cerr << "  " << int_to_string(sequence_count) << " reads, " << int_to_string((long long)size()) << " 16-mers\n\n";
+    const long long n_kmers = (long long)size();                      // resolves the multiple-copy rule (kmers.cpp:142-166)
+    // the 49 GiB of transient counting state are not needed for scoring (the reference's count map is
+    // likewise dead after hashing, it just never frees it: kmers.h:48-49)
+    if (ctx_) check(ctx_, fl_kmers_release_build_state(ctx_), "fl_kmers_release_build_state");
+    std::cerr << "  " << int_to_string(sequence_count) << " reads, " << int_to_string(n_kmers) << " 16-mers\n\n";
 }
 
 void Kmers::add_assembly_fasta(std::string filename) {

@@ -23,6 +23,8 @@
  *     Word index of padded base b is b/16;
  *   - qual: one byte per padded base, the raw FASTQ quality character (Phred+33); may be NULL
  *     when a k-mer reference is loaded (read.cpp:35-58 never touches it then);
+ *   - ascii: alternative to seq2b (+ nmask) for callers that hold text: one character per padded base;
+ *     the 2-bit packing of kmers.cpp:176-219 then happens on the device (k_pack_ascii);
  *   - nmask: 1 bit per padded base, bit (b & 31) of word b/32, set where the character was not
  *     one of ACGTacgt. Only reference sequences need it (kmers.cpp:199-219: the reverse encoder
  *     maps such characters to 0, i.e. NOT to the complement of the forward code); may be NULL.
@@ -73,6 +75,10 @@ typedef struct fl_batch {
     const uint32_t *seq2b;   /* [padded_bases/16] or NULL (Phred-only scoring never reads it) */
     const uint8_t *qual;     /* [padded_bases]    or NULL */
     const uint32_t *nmask;   /* [padded_bases/32] or NULL */
+    const char *ascii;       /* [padded_bases] or NULL: the bases as TEXT (what read.h:32 / kseq hand over),
+                                one byte per padded base (padding bytes are ignored). Used when seq2b is
+                                NULL: the library packs 2-bit codes (and the non-ACGT mask of reference
+                                sequences) on the DEVICE, so a host caller only copies bytes */
 } fl_batch;
 
 typedef struct fl_ctx fl_ctx;
@@ -163,13 +169,37 @@ typedef struct fl_summary {
     int64_t target, passed_bases, keeping, total_bases, rows_bases;
 } fl_summary;
 
-/* Whole block main.cpp:169-261 on one GPU. total_bases = sum of all input read lengths
- * (main.cpp:89), used by --keep_percent; pass -1 to use the context's own count. */
+/* Whole block main.cpp:169-261. total_bases = sum of the input read lengths THIS context was given
+ * (main.cpp:89; --keep_percent uses the sum over all shards); pass -1 to use the context's own count.
+ * On a context with a communicator (fl_comm_init) the call is collective: every rank calls it, the
+ * statistics, the base-weighted score histogram (13-bit digits, 5 levels) and the tie class at the cut-off
+ * are exchanged with NCCL on the context's stream (no host round trip in between), and every rank gets the
+ * same summary while its rows keep their own pass flags. Without a communicator the same code runs with
+ * the collectives degenerated to local copies. */
 int fl_finalize(fl_ctx *ctx, int64_t total_bases, fl_summary *out);
 
-/* Split-phase form for a read set sharded across GPUs (one context per GPU). The caller
- * all-reduces the small DEVICE buffers between phases (torch.distributed / NCCL); with one GPU
- * the phases can simply be called back to back. Buffers are caller-allocated device memory.
+/* ---- read set sharded across GPUs: one context + one rank per GPU ----------------- */
+/* The reference is a single thread (main.cpp:37-321); a sharded run couples its shards only through the
+ * block main.cpp:169-261 and through the shared Kmers object. One process per GPU or one thread per GPU.
+ * fl_comm_unique_id: rank 0 creates the 128-byte id (ncclGetUniqueId) and hands it to the other ranks by
+ * any means; fl_comm_init: ncclCommInitRank on the context's device (collective). */
+#define FL_COMM_ID_BYTES 128
+int fl_comm_unique_id(void *out128);
+int fl_comm_init(fl_ctx *ctx, const void *id128, int rank, int nranks);
+int fl_comm_destroy(fl_ctx *ctx);
+int fl_comm_info(const fl_ctx *ctx, int *rank, int *nranks);
+/* Kmers built on one rank, used by all (main.cpp:53-59 once per run): broadcasts the finished
+ * direct-address bitmap (512 MiB) from `root` over NVLink; collective. */
+int fl_kmers_broadcast(fl_ctx *ctx, int root);
+/* Sum of up to 24 host int64 over the ranks (e.g. the shards' read and base counts for the log lines of
+ * misc.cpp:47-49); collective, synchronises the context's stream. */
+int fl_comm_allreduce_i64_host(fl_ctx *ctx, int64_t *inout, int n);
+/* NCCL calls issued by this context so far. */
+uint64_t fl_comm_collective_count(const fl_ctx *ctx);
+
+/* Split-phase form of the same block for callers that bring their OWN transport (the CPU test double
+ * over gloo in tests/test_sharded_select.py; 8 levels of 256 bins): the caller all-reduces the small
+ * DEVICE buffers between phases. Buffers are caller-allocated device memory.
  *   1. fl_norm_partial1(ctx, sums, mins, maxs)         sums = f64[4]: n, sum(mean_q), passed_bases,
  *                                                       rows_bases; mins/maxs = f64[1]
  *                                                       -> all-reduce SUM / MIN / MAX
@@ -232,6 +262,9 @@ int fl_results_pass_dev(fl_ctx *ctx, void **dev_passed_final, uint64_t *n_rows);
 int fl_results_pass(fl_ctx *ctx, uint8_t *host_out, uint64_t cap, uint64_t *n_rows);
 
 /* ---- synthetic workloads (bench / tests only; deterministic, identical on host and device) -- */
+/* SURVEY 8d's generators as integer-only counter-based functions (filtlong_b200/csrc/fl_synth.h). The
+ * *_host flavours are also exported by the tiny libflsynth_host.so (no CUDA inside) for the CPU legs of
+ * bench.py. */
 /* Phred+33 quality string for padded arena `off/len`: per-base Q = clip(qbar[i] + z, 1, 50) with z
  * an integer-only approximately normal(0, 4) draw keyed by (seed, read index, position). */
 int fl_synth_qual_device(fl_ctx *ctx, uint64_t seed, uint32_t n, const uint64_t *dev_off,
@@ -242,12 +275,23 @@ void fl_synth_qual_host(uint64_t seed, uint32_t n, const uint64_t *off, const in
 /* Uniform random genome of n_bases (2-bit arena, one sequence at offset 0). */
 int fl_synth_genome_device(fl_ctx *ctx, uint64_t seed, uint64_t n_bases, uint32_t *dev_seq2b);
 void fl_synth_genome_host(uint64_t seed, uint64_t n_bases, uint32_t *seq2b);
-/* Reads sampled from that genome: read i = genome[start[i] .. start[i]+len[i]) on strand[i]
- * (1 = reverse complement) with substitution errors at rate err_ppm[i]/1e6 and, if junk_len[i] > 0,
- * a block of uniform random bases at [junk_pos[i], junk_pos[i]+junk_len[i]). */
+/* Assembly of n_contigs contigs of contig_bases uniform random bases each (contig c at padded offset
+ * c * fl_padded_len(contig_bases)), with n_ppm / 1e6 of its 1024-base blocks replaced by runs of N
+ * (code 0 in seq2b, bit set in nmask; nmask may be NULL). BASELINE config 5: 1000 x 3 Mbp, 2 % N. */
+int fl_synth_assembly_device(fl_ctx *ctx, uint64_t seed, uint32_t n_contigs, uint64_t contig_bases,
+                             uint32_t n_ppm, uint32_t *dev_seq2b, uint32_t *dev_nmask);
+void fl_synth_assembly_host(uint64_t seed, uint32_t n_contigs, uint64_t contig_bases, uint32_t n_ppm,
+                            uint32_t *seq2b, uint32_t *nmask);
+/* Reads sampled from that genome: read i is copied from the template genome[start[i], start[i] + span)
+ * (span = len + len/8 + 64, fl_synth_span) on strand[i] (1 = reverse complement) with per-base errors at
+ * rate err_ppm[i]/1e6 -- split 50/25/25 into substitutions / insertions / deletions when flags bit 0 is
+ * set (ONT / PacBio model), substitutions only otherwise (Illumina model) -- and, overriding the template,
+ * uniform random bases in [junk_pos[i], junk_pos[i]+junk_len[i]) (chimeric insert) and in the first
+ * adap5[i] / last adap3[i] positions (adapters). adap5 / adap3 may be NULL. */
+#define FL_SYNTH_INDELS 1u
 typedef struct fl_synth_reads {
     uint32_t n;
-    uint32_t reserved;
+    uint32_t flags;
     uint64_t genome_bases;
     const uint64_t *off;
     const int32_t *len;
@@ -255,11 +299,18 @@ typedef struct fl_synth_reads {
     const uint8_t *strand;
     const uint32_t *err_ppm;
     const int32_t *junk_pos, *junk_len;
+    const int32_t *adap5, *adap3;
 } fl_synth_reads;
 int fl_synth_reads_device(fl_ctx *ctx, uint64_t seed, const uint32_t *dev_genome2b,
                           const fl_synth_reads *dev_desc, uint64_t read_index_base, uint32_t *dev_seq2b);
 void fl_synth_reads_host(uint64_t seed, const uint32_t *genome2b, const fl_synth_reads *desc,
                          uint64_t read_index_base, uint32_t *seq2b);
+/* 2-bit arena -> ASCII bases (one byte per padded base, 'N' where nmask is set, 0 in the padding):
+ * what a caller holding text would hand to the char* boundary (read.h:32). */
+int fl_synth_ascii_device(fl_ctx *ctx, uint32_t n, const uint64_t *dev_off, const int32_t *dev_len,
+                          const uint32_t *dev_seq2b, const uint32_t *dev_nmask, uint8_t *dev_ascii);
+void fl_synth_ascii_host(uint32_t n, const uint64_t *off, const int32_t *len, const uint32_t *seq2b,
+                         const uint32_t *nmask, uint8_t *ascii);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
 const char *fl_version(void);

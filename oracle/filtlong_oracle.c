@@ -172,6 +172,12 @@ void orc_kmers_add_sequence(orc_kmers *k, const char *seq, size_t len, int multi
 
 int orc_kmers_contains(const orc_kmers *k, uint32_t kmer) { return tab_get(k, kmer) == STATE_SET; }
 
+/* Test hook: load an explicit set (e.g. one exported by the CUDA build at a size the CPU hashing of the
+ * short reads cannot follow), so that SCORING parity can still be checked against this restatement. */
+void orc_kmers_insert(orc_kmers *k, const uint32_t *kmers, size_t n) {
+    for (size_t i = 0; i < n; ++i) add_one_copy(k, kmers[i]);
+}
+
 uint64_t orc_kmers_size(const orc_kmers *k) { return k ? k->in_set : 0; }
 
 static int cmp_u32(const void *a, const void *b) {

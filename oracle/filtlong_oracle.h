@@ -28,6 +28,7 @@ void orc_kmers_free(orc_kmers *k);
  * or kmers.cpp:142-166 (1). */
 void orc_kmers_add_sequence(orc_kmers *k, const char *seq, size_t len, int require_multiple_copies);
 int orc_kmers_contains(const orc_kmers *k, uint32_t kmer);      /* kmers.cpp:170-172 */
+void orc_kmers_insert(orc_kmers *k, const uint32_t *kmers, size_t n);   /* test hook: m_kmers.insert of an explicit list */
 uint64_t orc_kmers_size(const orc_kmers *k);                    /* m_kmers.size() */
 size_t orc_kmers_dump(const orc_kmers *k, uint32_t *out, size_t cap); /* ascending order */
 /* bloom_filter.h:569-583 specialised to a 4-byte key, salt j of 13; and the table size */

@@ -112,6 +112,7 @@ def lib():
         L.orc_kmers_new.restype = C.c_void_p
         L.orc_kmers_free.argtypes = [C.c_void_p]
         L.orc_kmers_add_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int]
+        L.orc_kmers_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_kmers_contains.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_kmers_contains.restype = C.c_int
         L.orc_kmers_size.argtypes = [C.c_void_p]
@@ -159,6 +160,12 @@ class Kmers:
     def add_short_reads(self, seqs):
         for s in seqs:
             self.add_sequence(s, True)
+
+    def insert(self, kmers):
+        """Load an explicit list of 16-mers (numpy uint32)."""
+        import numpy as np
+        a = np.ascontiguousarray(kmers, dtype=np.uint32)
+        lib().orc_kmers_insert(self._h, a.ctypes.data, a.size)
 
     def __contains__(self, kmer):
         return bool(lib().orc_kmers_contains(self._h, kmer))

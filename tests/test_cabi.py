@@ -185,4 +185,46 @@ def test_synth_generators_are_deterministic_and_sane():
     out[:] = 0
     L.fl_synth_reads_host(3, capi.ptr(g), C.byref(d), 0, capi.ptr(out))
     rc = [(int(out[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(200)]
-    assert rc == [3 - c for c in codes[100:300]][::-1]
+    span = 200 + 200 // 8 + 64                        # fl_synth_span: the template a read may consume
+    assert rc == [3 - c for c in codes[100:100 + span]][::-1][:200]
+    # ONT model: 50/25/25 substitutions / insertions / deletions at the per-read rate, adapters at both ends
+    g2 = np.zeros(20000 // 16 + 1, dtype=np.uint32)
+    L.fl_synth_genome_host(2, 20000, capi.ptr(g2))
+    gc = np.array([(int(g2[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(20000)])
+    rl[0] = 8000; st[0] = 500; sd[0] = 0; er[0] = 100000
+    a5 = np.array([40], dtype=np.int32); a3 = np.array([30], dtype=np.int32)
+    d.flags = capi.SYNTH_INDELS; d.genome_bases = 20000
+    d.adap5, d.adap3 = capi.ptr(a5), capi.ptr(a3)
+    out = np.zeros(8064 // 16, dtype=np.uint32)
+    L.fl_synth_reads_host(7, capi.ptr(g2), C.byref(d), 5, capi.ptr(out))
+    out2 = np.zeros_like(out)
+    L.fl_synth_reads_host(7, capi.ptr(g2), C.byref(d), 5, capi.ptr(out2))
+    assert np.array_equal(out, out2)
+    rd = np.array([(int(out[i >> 4]) >> (30 - 2 * (i & 15))) & 3 for i in range(8000)])
+    # 16-mers of the read found in the template: far fewer than for an error-free copy, far more than chance
+    tmpl = {tuple(gc[i:i + 16]) for i in range(500, 500 + 9100)}
+    hits = sum(tuple(rd[i:i + 16]) in tmpl for i in range(40, 8000 - 30 - 16))
+    assert 0.05 * 7900 < hits < 0.45 * 7900, hits        # (1 - 0.1)^16 = 0.185 of the 16-mers survive a 10 % error rate
+    # assembly with runs of N, and its text form
+    nc, cb = 3, 5000
+    pad = int(L.fl_padded_len(cb))
+    seq = np.zeros(nc * pad // 16, dtype=np.uint32); nm = np.zeros(nc * pad // 32, dtype=np.uint32)
+    L.fl_synth_assembly_host(4, nc, cb, 200000, capi.ptr(seq), capi.ptr(nm))
+    aoff = (np.arange(nc, dtype=np.uint64) * pad); alen = np.full(nc, cb, dtype=np.int32)
+    txt = np.zeros(nc * pad, dtype=np.uint8)
+    L.fl_synth_ascii_host(nc, capi.ptr(aoff), capi.ptr(alen), capi.ptr(seq), capi.ptr(nm), capi.ptr(txt))
+    contig0 = txt[:cb].tobytes()
+    assert set(contig0) <= set(b"ACGTN") and txt[cb:pad].max() == 0
+    n_frac = sum(txt[c * pad:c * pad + cb].tobytes().count(b"N") for c in range(nc)) / (nc * cb)
+    assert 0.03 < n_frac < 0.5, n_frac
+    # N bases are whole 1024-base blocks (of the arena) and carry code 0
+    for c in range(nc):
+        t = txt[c * pad:c * pad + cb]
+        for b0 in range(0, cb, 1024):
+            blk = t[b0:min(b0 + 1024, cb)]
+            assert (blk == ord("N")).all() or not (blk == ord("N")).any() or (c * pad + b0) % 1024 != 0
+    # packing the text back through the library's host packer reproduces codes and mask
+    s2 = np.zeros_like(seq); n2 = np.zeros_like(nm)
+    for c in range(nc):
+        L.fl_pack_sequence(txt[c * pad:c * pad + cb].tobytes(), None, cb, c * pad, capi.ptr(s2), None, capi.ptr(n2))
+    assert np.array_equal(s2, seq) and np.array_equal(n2, nm)
