@@ -317,9 +317,7 @@ static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool wan
         FL_CUDA(c, S.seq.reserve(words + 4, 0, s));
         if (want_nmask) FL_CUDA(c, S.nmask.reserve((words >> 1) + 4, 0, s));
         FL_CUDA(c, cudaMemcpyAsync(S.ascii.p, h->ascii, (size_t)h->padded_bases, cudaMemcpyHostToDevice, s));
-        FL_TRY(fl_pack_ascii_device(c, S.ascii.p, h->padded_bases, S.seq.p, want_nmask ? S.nmask.p : nullptr, s));
-        v->seq2b = S.seq.p;
-        if (want_nmask) v->nmask = S.nmask.p;
+        v->ascii = S.ascii.p;            // packed by the caller on the COMPUTE stream (stage_pack): the copy stream only copies
     }
     if (want_qual && h->qual) {
         FL_CUDA(c, S.qual.reserve((size_t)h->padded_bases + 64, 0, s));
@@ -332,6 +330,16 @@ static int stage_host_batch(fl_ctx *c, const fl_batch *h, BatchView *v, bool wan
         FL_CUDA(c, cudaMemcpyAsync(S.nmask.p, h->nmask, words * 4, cudaMemcpyHostToDevice, s));
         v->nmask = S.nmask.p;
     }
+    return FL_OK;
+}
+
+// second half of a text hand-off: 2-bit codes (+ non-ACGT mask) from the staged characters, on the compute stream
+static int stage_pack(fl_ctx *c, BatchView *v, bool want_nmask, int slot) {
+    if (v->seq2b || !v->ascii) return FL_OK;
+    fl_ctx::Staging &S = c->stg[slot];
+    FL_TRY(fl_pack_ascii_device(c, v->ascii, v->padded_bases, S.seq.p, want_nmask ? S.nmask.p : nullptr, c->stream));
+    v->seq2b = S.seq.p;
+    if (want_nmask) v->nmask = S.nmask.p;
     return FL_OK;
 }
 
@@ -368,6 +376,7 @@ extern "C" int fl_kmers_add_batch(fl_ctx *c, const fl_batch *h, int multi) {
     BatchView v{};
     FL_TRY(staging_acquire(c, 0));
     FL_TRY(stage_host_batch(c, h, &v, true, false, true, 0, c->stream));
+    FL_TRY(stage_pack(c, &v, true, 0));
     FL_TRY(fl_kmers_add_view(c, v, multi));
     FL_CUDA(c, cudaStreamSynchronize(c->stream));   // staging buffers are reused by the next call
     return FL_OK;
@@ -406,6 +415,7 @@ extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
     FL_TRY(stage_host_batch(c, h, &v, kmer_mode, !kmer_mode, false, slot, c->copy_stream));
     FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
     FL_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+    FL_TRY(stage_pack(c, &v, false, slot));
     FL_TRY(fl_score_view(c, v));
     FL_CUDA(c, cudaEventRecord(c->stg[slot].consumed, c->stream));
     c->stg[slot].in_use = true;

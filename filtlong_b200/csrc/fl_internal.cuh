@@ -117,7 +117,7 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    int filter_kind = 2;                 // bit 0: word from the k-mer minimizer instead of a plain hash; bit 1: load the filter with ld.global.cg (FL_FILTER_KIND)
+    int filter_kind = 3;                 // bit 0: word from the k-mer's minimizer (loads de-duplicated per lane) instead of a plain hash; bit 1: ld.global.cg (FL_FILTER_KIND)
     bool use_filter = false;
     uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
     bool use_anchor = false;
@@ -162,6 +162,7 @@ struct fl_ctx {
     DevVec<uint32_t> sc_pack_seq, sc_pack_nmask;   // 2-bit codes / non-ACGT mask packed on the device from an ASCII DEVICE batch
     DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer
     DevVec<uint32_t> sc_order;       // rows in descending-length bucket order
+    DevVec<int32_t> sc_items;        // length of each k_kmer_window item: the batch's reads, then its rows
     DevVec<unsigned long long> sc_u64a, sc_u64b, sc_u64c;
     DevVec<uint32_t> sc_u32a;
     DevVec<unsigned long long> sc_scan;   // block sums of fl_exclusive_scan_u64

@@ -20,6 +20,8 @@
 //    are NOT re-probed: a matching 16-mer never overlaps a bad range, so a child's mask is the
 //    parent's mask restricted to the child range; the reference re-runs the whole
 //    constructor instead (read.cpp:137).
+#include <cmath>
+
 #include "fl_device.cuh"
 
 namespace {
@@ -37,9 +39,8 @@ struct ProbeArgs {
     const uint32_t *seq2b;
     const uint64_t *off;
     const int32_t *len;
-    const unsigned long long *tile_start;   // [n+1]
+    const unsigned long long *tile_start;   // [n+1]; [n] = number of tiles
     uint32_t n;
-    unsigned long long n_tiles;
     const uint32_t *bitmap;
     const uint32_t *anchor;                  // position-anchored table (fl_anchor_slot), used when ANCH
     const unsigned long long *filter;        // L2-resident pre-filter (fl_kmers.cu), used when FILT
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
     return __ldg(p);
 }
 
-template <int MODE, bool FILT, bool ANCH>
+template <int MODE, int FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     (void)pol_last;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long tile = warp; tile < a.n_tiles; tile += n_warps) {
+    const unsigned long long n_tiles = a.tile_start[a.n];      // read on the device: no host round trip between the scan and the launch
+    for (unsigned long long tile = warp; tile < n_tiles; tile += n_warps) {
         const uint32_t s = fl_find_seq(a.tile_start, a.n, tile);
         const int L = a.len[s];
         const unsigned long long off = a.off[s];
@@ -137,8 +139,45 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
                 uint32_t go = 0xFFFFu;                // which of the 16 k-mers still need the exact bitmap
-                if (FILT) {
-                    // 16 independent loads from the 64 MiB pre-filter (kept in L2): most k-mers of a
+                if (FILT == 2) {
+                    // Pre-filter keyed by the 16-mer's MINIMIZER (smallest hashed 11-mer of its six, fl_filter_slot
+                    // kind 1): consecutive 16-mers of a lane mostly share it, and a lane only issues a load when the
+                    // word CHANGES (~1 in 3.5): the probe was bound by the L1TEX sector-request rate of one random
+                    // 8-byte load per 16-mer (ncu: L1TEX 86 %), not by bytes. The hashed 11-mers slide along the
+                    // lane's run, so each 16-mer costs one new hash and a 6-way minimum.
+                    unsigned long long f[16];
+                    uint32_t hq[6];                      // hashed 11-mers at run positions q-5 .. q
+                    auto h11 = [&](int q) -> uint32_t {  // 11-mer starting at base q (0..37) of the lane's 48 loaded bases
+                        const uint32_t x = q < 16 ? __funnelshift_l(w.w1, w.w0, 2 * q) : (q < 32 ? __funnelshift_l(w.w2, w.w1, 2 * (q - 16)) : (w.w2 << (2 * (q - 32))));
+                        return (x >> 10) * 0x9E3779B1u;
+                    };
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) hq[t] = h11(half * 16 + t);
+                    uint32_t wprev = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        hq[5] = h11(half * 16 + i + 5);
+                        uint32_t mn = hq[0];
+#pragma unroll
+                        for (int t = 1; t < 6; ++t) mn = hq[t] < mn ? hq[t] : mn;
+#pragma unroll
+                        for (int t = 0; t < 5; ++t) hq[t] = hq[t + 1];
+                        const uint32_t word = (mn * 0x85EBCA6Bu) >> (32 - a.filter_log2_words);
+                        const bool live = half * 16 + i < nvalid;
+                        if (live && word != wprev) f[i] = __ldcg(a.filter + word);
+                        else f[i] = (live && i > 0) ? f[i > 0 ? i - 1 : 0] : 0ull;
+                        wprev = live ? word : 0xFFFFFFFFu;
+                    }
+                    go = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t kk = fl_kmer_at(w, half * 16 + i);
+                        const uint32_t h2 = (kk ^ (kk >> 15)) * 0x85EBCA6Bu;
+                        const unsigned long long fb = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
+                        go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
+                    }
+                } else if (FILT) {
+                    // 16 independent loads from the 32 MiB pre-filter (kept in L2): most k-mers of a
                     // noisy read are absent and stop here, without touching HBM
                     unsigned long long f[16];
 #pragma unroll
@@ -230,299 +269,457 @@ __global__ void k_tiles_of(const int32_t *__restrict__ len, uint32_t n, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
-// k-mer mode, kernels B: everything else from the 1-bit mask
+// k-mer mode, kernels B: everything else from the 1-bit mask, one WARP per read / per row.
+//
+//   k_kmer_scan<EMIT>  one warp per read streams the mask (32 words = 1024 bases per step, coalesced):
+//                      first / last base in a k-mer (read.cpp:75-84), the zero runs that become bad ranges
+//                      (read.cpp:89-117) found with ballots and shuffles (a run that crosses word boundaries
+//                      is closed by the lane holding its terminating one-bit), child ranges (read.cpp:119-130).
+//                      Pass 1 counts, an exclusive scan places the rows, pass 2 (EMIT) writes them.
+//   k_kmer_window      one warp per row: mean = 100 * popcount / len (the reference sums exact 1.0s), and the
+//                      window quality of read.cpp:216-236 bit for bit without walking the row (see below).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int find_next(const uint32_t *__restrict__ m, int p, int end, bool want_one) {
-    while (p < end) {
-        uint32_t w = m[p >> 5];
-        if (!want_one) w = ~w;
-        w &= 0xFFFFFFFFu << (p & 31);
-        if (w) {
-            int q = (p & ~31) + __ffs(w) - 1;
-            return q < end ? q : end;
-        }
-        p = (p & ~31) + 32;
-    }
-    return end;
-}
-
-// Walks the bad ranges of read.cpp:89-117 in order and reports child ranges (read.cpp:119-130).
-// F(start, end, child_index). Returns n_child; *n_bad_out = m_bad_ranges.size().
-template <typename F>
-__device__ __forceinline__ int enumerate_children(const uint32_t *__restrict__ m, int L, int first, int last,
-                                                  const fl_params &p, int *n_bad_out, F emit) {
-    int n_bad = 0, n_child = 0, rs = 0;
-    auto bad = [&](int s, int e) {
-        ++n_bad;
-        if (s - rs > 0) emit(rs, s, n_child++);
-        rs = e;
-    };
-    if (first < 0) {
-        // no base is in a k-mer: one zero run [0, L); trimming adds nothing (read.cpp:107,112)
-        if (p.split_set && L > 0 && L >= p.split) bad(0, L);
-    } else {
-        const bool lead_is_split = p.split_set && first >= p.split && first > 0;
-        const bool tail_is_split = p.split_set && (L - last) >= p.split && last < L;
-        if (lead_is_split) bad(0, first);
-        else if (p.trim && first > 0) bad(0, first);                     // read.cpp:107-111
-        if (p.split_set) {                                               // read.cpp:89-103, runs inside [first, last)
-            int i = first;
-            while (i < last) {
-                int z = find_next(m, i, last, false);
-                if (z >= last) break;
-                int o = find_next(m, z, last, true);
-                if (o - z >= p.split) bad(z, o);
-                i = o;
-            }
-        }
-        if (tail_is_split) bad(last, L);
-        else if (p.trim && last < L) bad(last, L);                       // read.cpp:112-116
-    }
-    if (n_bad > 0 && L - rs > 0) emit(rs, L, n_child++);                 // read.cpp:127-129
-    *n_bad_out = n_bad;
-    return n_child;
-}
-
-struct KmerArgs {
+struct ScanArgs {
     const uint32_t *mask;
     const uint64_t *off;
     const int32_t *len;
     uint32_t n;
     fl_params p;
     int32_t *r_len, *r_first, *r_last, *r_nbad, *r_nchild;
-    double *r_mean, *r_window;
-    uint8_t *r_passed;
-    unsigned long long *r_rowstart;
-    unsigned long long *rows_per_read;   // scratch [n]
+    unsigned long long *r_rowstart;       // COUNT: row_base + r (final when nothing can have children). EMIT: in = batch-local exclusive scan, out = + row_base
+    unsigned long long *rows_per_read;    // COUNT out [n]
+    int32_t *item_len;                    // COUNT: [r] = L (the parent item). EMIT: [n + row] = child length, 0 for the row of a childless read
+    uint32_t *w_parent;                   // EMIT out, offset to this batch's first row
+    int32_t *w_start, *w_end;
     unsigned long long read_base, row_base;
 };
 
-// B1: per read -- first/last base in a k-mer, number of bad ranges and children
-__global__ void __launch_bounds__(256) k_kmer_ranges(KmerArgs a) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    const int L = a.len[r];
-    const uint32_t *m = a.mask + (a.off[r] >> 5);
-    int first = -1, last = -1;
-    const int nw = (L + 31) >> 5;
-    for (int w = 0; w < nw; ++w) {                       // read.cpp:77-84
-        uint32_t x = m[w];
-        if (x) {
-            if (first < 0) first = (w << 5) + __ffs(x) - 1;
-            last = (w << 5) + 32 - __clz(x);
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lower = (1u << lane) - 1u;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const bool split_set = a.p.split_set != 0, trim = a.p.trim != 0;
+    const int split = a.p.split;
+    for (size_t r = warp; r < a.n; r += n_warps) {
+        const int L = a.len[r];
+        const uint32_t *m = a.mask + (a.off[r] >> 5);
+        const int n_words = (L + 31) >> 5;
+        unsigned long long rs_row = 0;
+        if (EMIT) {
+            rs_row = a.r_rowstart[r];
+            if (lane == 0) a.r_rowstart[r] = rs_row + a.row_base;
+            if (a.r_nchild[r] == 0) {                            // the read is its own row (main.cpp:140)
+                if (lane == 0) {
+                    a.w_parent[rs_row] = (uint32_t)(a.read_base + r);
+                    a.w_start[rs_row] = 0;
+                    a.w_end[rs_row] = L;
+                    a.item_len[a.n + rs_row] = 0;                // scored by the parent's item
+                }
+                continue;
+            }
         }
-    }
-    int n_bad = 0, n_child = 0;
-    if (a.p.trim || a.p.split_set)
-        n_child = enumerate_children(m, L, first, last, a.p, &n_bad, [](int, int, int) {});
-    a.r_len[r] = L;
-    a.r_first[r] = first;
-    a.r_last[r] = last;
-    a.r_nbad[r] = n_bad;
-    a.r_nchild[r] = n_child;
-    a.rows_per_read[r] = n_child > 0 ? (unsigned long long)n_child : 1ull;
-    a.r_rowstart[r] = a.row_base + r;   // final when nothing can have children; else replaced by the scan
-}
-
-// B2: per read -- row descriptors (children, or the read itself)
-struct RowArgs {
-    const uint32_t *mask;
-    const uint64_t *off;
-    const int32_t *len;
-    uint32_t n;
-    fl_params p;
-    const int32_t *r_first, *r_last, *r_nchild;
-    unsigned long long *r_rowstart;             // in: exclusive scan of rows per read (batch-local); out: + row_base
-    uint32_t *w_parent;                         // offset to this batch's first row
-    int32_t *w_start, *w_end, *w_len;
-    unsigned long long read_base, row_base;
-};
-
-__global__ void __launch_bounds__(256) k_kmer_rows(RowArgs a) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= a.n) return;
-    const int L = a.len[r];
-    const unsigned long long rs = a.r_rowstart[r];
-    a.r_rowstart[r] = rs + a.row_base;
-    if (a.r_nchild[r] == 0) {
-        a.w_parent[rs] = (uint32_t)(a.read_base + r);
-        a.w_start[rs] = 0;
-        a.w_end[rs] = L;
-        a.w_len[rs] = L;
-        return;
-    }
-    const uint32_t *m = a.mask + (a.off[r] >> 5);
-    int nb;
-    enumerate_children(m, L, a.r_first[r], a.r_last[r], a.p, &nb, [&](int s, int e, int c) {
-        a.w_parent[rs + c] = (uint32_t)(a.read_base + r);
-        a.w_start[rs + c] = s;
-        a.w_end[rs + c] = e;
-        a.w_len[rs + c] = e - s;
-    });
-}
-
-// B3: per row -- mean and window quality from the mask range [S, E) of the parent read.
-// The k-mer-mode quality of a base is exactly 0.0 or 1.0 (read.cpp:42,55), so the mean's sequential
-// sum is an exact integer, and the window recurrence adds / subtracts r = 1.0 / ws or 0.0 in the
-// reference's order (read.cpp:226-232) -- bit-identical, including its rounding drift.
-template <bool RUNS>
-__device__ __forceinline__ void kmer_row_stats(const uint32_t *__restrict__ m, int S, int E, int ws, double *mean_out,
-                                               double *window_out) {
-    const int len = E - S;
-    // popcount of [S, E)
-    long long hits = 0;
-    {
-        int p = S;
-        while (p < E) {
-            uint32_t w = m[p >> 5] & (0xFFFFFFFFu << (p & 31));
-            int wend = (p & ~31) + 32;
-            if (wend > E) w &= 0xFFFFFFFFu >> (wend - E);
-            hits += __popc(w);
-            p = wend;
-        }
-    }
-    const double mean = 100.0 * (double)hits / (double)len;             // read.cpp:208-213
-    if (len <= ws) {                                                     // read.cpp:217-218
-        *mean_out = mean;
-        *window_out = mean;
-        return;
-    }
-    const double wsd = (double)ws;
-    const double rq = 1.0 / wsd;                                         // qualities[i] / window_size with q == 1.0
-    long long c0 = 0;
-    {
-        int p = S;
-        const int e0 = S + ws;
-        while (p < e0) {
-            uint32_t w = m[p >> 5] & (0xFFFFFFFFu << (p & 31));
-            int wend = (p & ~31) + 32;
-            if (wend > e0) w &= 0xFFFFFFFFu >> (wend - e0);
-            c0 += __popc(w);
-            p = wend;
-        }
-    }
-    double w = (double)c0 / wsd;                                         // read.cpp:220-223
-    double best = w;
-    int pin = S + ws, pout = S;
-    // scalar steps until the incoming position is word aligned
-    auto step = [&](unsigned bin, unsigned bout) {
-        w -= bout ? rq : 0.0;                                            // read.cpp:229
-        w += bin ? rq : 0.0;                                             // read.cpp:230
-        if (w < best) best = w;
-    };
-    for (; (pin & 31) && pin < E; ++pin, ++pout)
-        step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
-    if (pin + 32 <= E) {
-        const unsigned sh = (unsigned)(pout & 31);       // constant from here on
-        int ow_idx = pout >> 5;
-        uint32_t olo = m[ow_idx];
-        for (; pin + 32 <= E; pin += 32, pout += 32) {
-            const uint32_t inw = m[pin >> 5];
-            const uint32_t ohi = m[ow_idx + 1];          // within the parent's padded mask: pout + 32 + 31 < pin + 32 <= E
-            const uint32_t outw = __funnelshift_r(olo, ohi, sh);
-            if (!RUNS) {
-#pragma unroll
-                for (int t = 0; t < 32; ++t) step((inw >> t) & 1u, (outw >> t) & 1u);
-            } else {
-                // Long rows are the serial tail; they run in k_kmer_stats_long with ONE active lane per warp
-                // (no divergence) and walk the word by RUNS: a step with
-                // both bits 0 adds and subtracts 0.0 (no change); a step with both bits 1 maps w to
-                // g(w) = fl(fl(w - r) + r), and once g(w) == w every further (1,1) step is a no-op
-                // too, so g is applied until its fixed point (almost always at once); only steps
-                // whose bits differ really move w. Same values as the bit loop, step for step. (With 32
-                // rows per warp the data-dependent trip counts diverge and this loses -- measured.)
-                const uint32_t diff = inw ^ outw, both = inw & outw;
-                int t = 0;
-                while (t < 32) {
-                    const uint32_t rem = diff >> t;
-                    const int nd = rem ? t + (__ffs(rem) - 1) : 32;      // next step whose bits differ
-                    if (nd > t) {
-                        const uint32_t stretch = (nd - t == 32) ? 0xFFFFFFFFu : (((1u << (nd - t)) - 1u) << t);
-                        int c11 = __popc(both & stretch);
-                        while (c11-- > 0) {
-                            const double w2 = (w - rq) + rq;                 // read.cpp:229-230, both qualities 1
-                            if (w2 == w) break;
-                            w = w2;
-                            if (w < best) best = w;
-                        }
-                    }
-                    if (nd >= 32) break;
-                    if ((inw >> nd) & 1u) { w -= 0.0; w += rq; }             // base enters a k-mer match
-                    else { w -= rq; w += 0.0; }                              // base leaves one
-                    if (w < best) best = w;
-                    t = nd + 1;
+        int first = -1, last = -1, n_bad = 0, n_child = 0, rs = 0;
+        int carry_open = 0;                                      // length of the zero run that ends at the end of the previous step
+        bool seen_one = false;
+        auto child = [&](int s, int e, int idx) {
+            if (EMIT) {
+                a.w_parent[rs_row + idx] = (uint32_t)(a.read_base + r);
+                a.w_start[rs_row + idx] = s;
+                a.w_end[rs_row + idx] = e;
+                a.item_len[a.n + rs_row + idx] = e - s;
+            }
+        };
+        for (int wb = 0; wb < n_words; wb += 32) {
+            const int wi = wb + (int)lane;
+            const uint32_t x = wi < n_words ? __ldg(m + wi) : 0u;
+            const unsigned nz = __ballot_sync(0xffffffffu, x != 0u);
+            const int tzc = x ? __clz(x) : 32, lzc = x ? __ffs(x) - 1 : 32;
+            const unsigned lo_nz = nz & lower;
+            const int j = lo_nz ? 31 - __clz(lo_nz) : 0;
+            const int tz_j = __shfl_sync(0xffffffffu, tzc, j);
+            const int open_prev = lo_nz ? tz_j + 32 * ((int)lane - j - 1) : carry_open + 32 * (int)lane;
+            const int o = (wb + (int)lane) * 32 + lzc;           // position of this word's lowest one-bit
+            const int runlen = open_prev + lzc, z = o - runlen;
+            const bool is_first = x && !seen_one && !lo_nz;      // the run is [0, first): read.cpp:106-111 decides
+            const bool b_emit = x && (is_first ? ((split_set && o >= split && o > 0) || (trim && o > 0))
+                                               : (split_set && runlen >= split));
+            // zero runs strictly inside the word (shorter than 32: only a --split below 32 can want them)
+            int n_in = 0, in_last_e = 0;
+            if (split_set && split < 32 && x) {
+                uint32_t y = ~x & (0xFFFFFFFFu << lzc) & (0xFFFFFFFFu >> tzc);
+                while (y) {
+                    const int s0 = __ffs(y) - 1;
+                    const uint32_t rest = ~(y >> s0);
+                    const int ln = __ffs(rest) - 1;              // run length (a one-bit follows inside the word)
+                    if (ln >= split) { ++n_in; in_last_e = wi * 32 + s0 + ln; }
+                    y &= ~(((1u << ln) - 1u) << s0);
                 }
             }
-            olo = ohi;
-            ++ow_idx;
+            const bool emits = b_emit || n_in > 0;
+            const int my_last_e = n_in > 0 ? in_last_e : o;
+            const unsigned em = __ballot_sync(0xffffffffu, emits);
+            const unsigned lo_em = em & lower;
+            const int pe = lo_em ? 31 - __clz(lo_em) : 0;
+            const int prev_e = __shfl_sync(0xffffffffu, my_last_e, pe);
+            const int rs_mine = lo_em ? prev_e : rs;
+            const int b_child = (b_emit && z - rs_mine > 0) ? 1 : 0;
+            const int my_children = b_child + n_in;              // every in-word run is preceded by a one-bit: a child always
+            int incl = my_children;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += t;
+            }
+            if (EMIT && emits) {
+                int idx = n_child + incl - my_children, prev = rs_mine;
+                if (b_emit) {
+                    if (b_child) child(prev, z, idx++);
+                    prev = o;
+                }
+                if (n_in > 0) {
+                    uint32_t y = ~x & (0xFFFFFFFFu << lzc) & (0xFFFFFFFFu >> tzc);
+                    while (y) {
+                        const int s0 = __ffs(y) - 1;
+                        const uint32_t rest = ~(y >> s0);
+                        const int ln = __ffs(rest) - 1;
+                        if (ln >= split) {
+                            child(prev, wi * 32 + s0, idx++);
+                            prev = wi * 32 + s0 + ln;
+                        }
+                        y &= ~(((1u << ln) - 1u) << s0);
+                    }
+                }
+            }
+            int my_bad = (b_emit ? 1 : 0) + n_in;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) my_bad += __shfl_xor_sync(0xffffffffu, my_bad, d);
+            n_bad += my_bad;
+            n_child += __shfl_sync(0xffffffffu, incl, 31);
+            if (em) rs = __shfl_sync(0xffffffffu, my_last_e, 31 - __clz(em));
+            if (nz) {
+                const int top = 31 - __clz(nz);
+                const int tz_top = __shfl_sync(0xffffffffu, tzc, top);
+                carry_open = tz_top + 32 * (31 - top);
+                last = (wb + top) * 32 + 32 - tz_top;                                       // read.cpp:81-84
+                if (!seen_one) first = __shfl_sync(0xffffffffu, o, __ffs(nz) - 1);          // read.cpp:77-80
+                seen_one = true;
+            } else {
+                carry_open += 1024;
+            }
+        }
+        // the tail [last, L) and the closing child (read.cpp:112-116, 127-129)
+        if (first < 0) {
+            if (split_set && L > 0 && L >= split) n_bad = 1;     // one zero run [0, L): a bad range without children
+        } else {
+            const bool tail_bad = last < L && ((split_set && (L - last) >= split) || trim);
+            if (tail_bad) {
+                ++n_bad;
+                if (last - rs > 0) { if (lane == 0) child(rs, last, n_child); ++n_child; }
+                rs = L;
+            }
+            if (n_bad > 0 && L - rs > 0) { if (lane == 0) child(rs, L, n_child); ++n_child; }
+        }
+        if (!EMIT && lane == 0) {
+            a.r_len[r] = L;
+            a.r_first[r] = first;
+            a.r_last[r] = last;
+            a.r_nbad[r] = n_bad;
+            a.r_nchild[r] = n_child;
+            a.rows_per_read[r] = n_child > 0 ? (unsigned long long)n_child : 1ull;
+            a.r_rowstart[r] = a.row_base + r;
+            a.item_len[r] = L;
         }
     }
-    for (; pin < E; ++pin, ++pout)
-        step((m[pin >> 5] >> (pin & 31)) & 1u, (m[pout >> 5] >> (pout & 31)) & 1u);
-    if (best < 0.5 / wsd) best = 0.0;                                    // read.cpp:233-234
-    *mean_out = mean;
-    *window_out = 100.0 * best;
 }
 
-struct StatArgs {
-    const uint32_t *mask;
-    const uint64_t *off;          // per batch read
-    const uint32_t *order;        // rows in descending length order
-    uint32_t n_rows;
-    fl_params p;
-    // rows (batch-local indexing): parent is a GLOBAL read index; read_base converts to batch-local
-    const uint32_t *w_parent;
-    const int32_t *w_start, *w_end;
-    double *w_mean, *w_window;
-    uint8_t *w_passed;
-    unsigned long long read_base;
-    // when non-null: rows that are whole reads copy the parent's statistics instead of recomputing
-    const int32_t *r_nchild;
-    const double *r_mean, *r_window;
-    const uint8_t *r_passed;
+// ---------------------------------------------------------------------------------------------
+// Window quality in k-mer mode (read.cpp:216-236 on qualities in {0, 1}) WITHOUT walking the row.
+//
+// The reference's chain:  w0 = fl(c0 / ws);  per step  w -= out ? rq : 0;  w += in ? rq : 0;  best = min(best, w),
+// rq = fl(1 / ws). With c the window's hit count (an integer prefix sum of the mask: parallel):
+//  (1) inside one binade whose grid does not put rq exactly half way between two grid points ("tie binade")
+//      adding / subtracting rq moves w by exactly R = rq rounded to the grid -- inverse operations;
+//  (2) subtracting rq across a binade's floor (onto the finer grid) and adding it back returns to the same value;
+//  (3) hence from an ANCHOR (w_a, c_a) every value the chain takes at a level c it reaches by moves below the
+//      highest level visited so far, outside tie binades, is one function F(c): walk down from the anchor (or up,
+//      on the anchor's grid). The chain's minimum over such an EPOCH is F(min c): one integer reduction, one
+//      short walk (grid jumps inside a binade, one true subtraction per binade floor);
+//  (4) not reversible: an addition that reaches a level not visited since the anchor AND next to a binade edge
+//      (it enters the coarser grid above, or leaves the binade's lowest level), and anything inside a tie binade
+//      (round-half-even looks at the parity of w). A 32-step word whose count range does either is walked with
+//      the reference's own double operations and a new epoch starts from the value it produced. Rare: a few
+//      record levels per row; for ws = 250 the only tie binade is [2^-5, 2^-4), windows with 8..15 hits.
+// tests/models/kmer_window_model.c is the scalar model of exactly this procedure (fuzzed against the reference
+// recurrence: tests/test_kmer_window_model.py); the kernel below is its transcription, 32 words per iteration.
+// ---------------------------------------------------------------------------------------------
+#define KW_MAX_ZONES 8
+#define KW_MAX_EDGES 16
+
+struct KwConsts {
+    double rq;
+    unsigned long long mant_rq;               // 53-bit significand of rq
+    int e_rq;                                 // rq in [2^e_rq, 2^(e_rq+1))
+    int n_zones, n_edges;
+    int zlo[KW_MAX_ZONES], zhi[KW_MAX_ZONES]; // count intervals whose values may lie in a tie binade (+- one level)
+    int elo[KW_MAX_EDGES], ehi[KW_MAX_EDGES]; // count intervals around the binade edges 2^e / rq (+- two levels)
 };
 
-// Measured (profiles/r01 launch lists): walking long rows by runs with one lane per warp
-// (k_kmer_stats_long) is 3x SLOWER on noisy hit masks than the unrolled bit loop, so every row takes
-// the bit loop; the threshold is kept only so the experiment can be repeated.
-#define FL_LONG_ROW 0x7FFFFFFF
+struct KwAnchor {
+    double w;
+    long long wb, rint, lo, hi;
+    int c, c_edge;
+    bool lattice;
+};
 
-__device__ __forceinline__ bool stat_row(const StatArgs &a, uint32_t row, bool long_pass) {
-    const uint32_t r = (uint32_t)(a.w_parent[row] - a.read_base);
-    const int S = a.w_start[row], E = a.w_end[row];
-    const bool is_long = (E - S) >= FL_LONG_ROW;
-    if (is_long != long_pass) return is_long;
-    if (a.r_nchild && a.r_nchild[r] == 0) {
-        a.w_mean[row] = a.r_mean[r];
-        a.w_window[row] = a.r_window[r];
-        a.w_passed[row] = a.r_passed[r];
-        return is_long;
+// grid parameters of the binade of w; false if it has none (rq's own binade and below -- arithmetic there is exact -- or a tie binade)
+__device__ __forceinline__ bool kw_binade(const KwConsts &k, double w, long long &wb, long long &rint, long long &lo, long long &hi) {
+    if (!(w > 0.0)) return false;
+    const long long b = __double_as_longlong(w);
+    const int e = (int)((b >> 52) & 0x7FF) - 1023;
+    const int s = e - k.e_rq;
+    if (s < 1 || s > 52) return false;
+    const unsigned long long half = 1ull << (s - 1);
+    if ((k.mant_rq & ((1ull << s) - 1ull)) == half) return false;
+    wb = b;
+    rint = (long long)((k.mant_rq + half) >> s);
+    lo = (long long)(e + 1023) << 52;
+    hi = lo + (1ll << 52);
+    return true;
+}
+
+// floor(x / y) for 0 <= x < 2^53, 0 < y < 2^53 without a 64-bit integer division
+__device__ __forceinline__ long long kw_floor_div(long long x, long long y) {
+    long long q = (long long)((double)x / (double)y);
+    if (q * y > x) --q;
+    else if ((q + 1) * y <= x) ++q;
+    return q;
+}
+
+__device__ __forceinline__ void kw_set_anchor(KwAnchor &a, const KwConsts &k, double w, int c) {
+    a.w = w;
+    a.c = c;
+    a.lattice = kw_binade(k, w, a.wb, a.rint, a.lo, a.hi);
+    a.c_edge = c;                                              // no usable grid: any level above the anchor ends the epoch
+    if (a.lattice) a.c_edge = c + (int)kw_floor_div(a.hi - 2 - a.wb, a.rint);
+}
+
+// F(c) for c <= a.c_edge: the chain's value at level c inside the anchor's epoch
+__device__ __forceinline__ double kw_eval(const KwAnchor &a, const KwConsts &k, int c) {
+    if (c >= a.c) return a.lattice ? __longlong_as_double(a.wb + a.rint * (long long)(c - a.c)) : a.w;
+    double w = a.w;
+    int cur = a.c;
+    while (cur > c) {
+        long long wb, rint, lo, hi;
+        if (kw_binade(k, w, wb, rint, lo, hi)) {
+            long long room = kw_floor_div(wb - (lo + 1), rint);      // levels that can be descended on the grid (value stays >= 2^e + ulp)
+            if (room > (long long)(cur - c)) room = cur - c;
+            if (room > 0) {
+                w = __longlong_as_double(wb - rint * room);
+                cur -= (int)room;
+                continue;
+            }
+        }
+        w = w - k.rq;                                                // read.cpp:229: across the binade floor
+        --cur;
     }
-    const uint32_t *m = a.mask + (a.off[r] >> 5);
-    double mean, window;
-    if (long_pass) kmer_row_stats<true>(m, S, E, a.p.window_size, &mean, &window);
-    else kmer_row_stats<false>(m, S, E, a.p.window_size, &mean, &window);
-    a.w_mean[row] = mean;
-    a.w_window[row] = window;
-    a.w_passed[row] = fl_hard_cutoffs(a.p, E - S, mean, window);
-    return is_long;
+    return w;
 }
 
-__global__ void __launch_bounds__(256) k_kmer_stats(StatArgs a) {
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.n_rows; it += T) stat_row(a, a.order[it], false);
+struct WinArgs {
+    const uint32_t *mask;
+    const uint64_t *off;                    // per batch read
+    const int32_t *len;
+    const uint32_t *order;                  // items in descending length order
+    uint32_t n_items, n_reads;              // items [0, n_reads): the reads themselves; [n_reads, n_items): rows (batch-local)
+    fl_params p;
+    KwConsts k;
+    const int32_t *r_nchild;
+    const unsigned long long *r_rowstart;   // global row index of a read's first row
+    unsigned long long row_base, read_base;
+    const uint32_t *w_parent;               // batch-local row arrays
+    const int32_t *w_start, *w_end;
+    double *r_mean, *r_window;              // batch-local outputs per read / per row
+    uint8_t *r_passed;
+    double *w_mean, *w_window;
+    uint8_t *w_passed;
+    unsigned long long *work;               // shared item counter
+};
+
+// bits [pos, pos + 32) of a mask whose last valid word is m[last_word]
+__device__ __forceinline__ uint32_t kw_bits(const uint32_t *__restrict__ m, long long pos, int last_word) {
+    const int wi = (int)(pos >> 5);
+    const uint32_t lo = __ldg(m + (wi <= last_word ? wi : last_word));
+    const uint32_t hi = __ldg(m + (wi + 1 <= last_word ? wi + 1 : last_word));
+    return __funnelshift_r(lo, hi, (unsigned)pos & 31u);
 }
 
-// one warp per long row, lane 0 only: rows are ordered longest first, so the long ones are a prefix
-__global__ void __launch_bounds__(32) k_kmer_stats_long(StatArgs a) {
-    if (threadIdx.x != 0) return;
-    for (size_t it = blockIdx.x; it < a.n_rows; it += gridDim.x)
-        if (!stat_row(a, a.order[it], true)) break;
+// popcount of bits [S, S + n) of the mask, by the whole warp
+__device__ __forceinline__ int kw_popcount(const uint32_t *__restrict__ m, int S, int n, int last_word, unsigned lane) {
+    int cnt = 0;
+    for (int j = (int)lane * 32; j < n; j += 1024) {
+        uint32_t v = kw_bits(m, (long long)S + j, last_word);
+        if (n - j < 32) v &= (1u << (n - j)) - 1u;
+        cnt += __popc(v);
+    }
+    return __reduce_add_sync(0xffffffffu, cnt);
 }
 
-__global__ void k_iota(uint32_t *p, uint32_t n, uint32_t base) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = base + i;
+__global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
+    // nibble table: 4 steps with pure-plus bits p and pure-minus bits q (p & q == 0) ->
+    // (delta + 4) | (lowest after-step partial sum + 4) << 4 | (highest + 4) << 8
+    __shared__ unsigned short lut[256];
+    {
+        const int p = threadIdx.x & 15, q = threadIdx.x >> 4;
+        int d = 0, mn = 99, mx = -99;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            d += ((p >> t) & 1) - ((q >> t) & 1);
+            mn = d < mn ? d : mn;
+            mx = d > mx ? d : mx;
+        }
+        lut[threadIdx.x & 255] = (unsigned short)((d + 4) | ((mn + 4) << 4) | ((mx + 4) << 8));
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const KwConsts &k = a.k;
+    const int ws = a.p.window_size;
+    const double wsd = (double)ws;
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(a.work, 1ull);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= a.n_items) break;
+        const uint32_t idx = a.order[it];
+        uint32_t r;
+        int S, E;
+        long long row = -1;                                        // batch-local row this item writes (if any)
+        const bool is_read = idx < a.n_reads;
+        if (is_read) {
+            r = idx;
+            S = 0;
+            E = a.len[r];
+            if (a.r_nchild[r] == 0) row = (long long)(a.r_rowstart[r] - a.row_base);
+        } else {
+            row = (long long)(idx - a.n_reads);
+            r = (uint32_t)(a.w_parent[row] - a.read_base);
+            if (a.r_nchild[r] == 0) continue;                      // scored by the read's own item
+            S = a.w_start[row];
+            E = a.w_end[row];
+        }
+        const int len = E - S;
+        const uint32_t *m = a.mask + (a.off[r] >> 5);
+        const int last_word = ((((a.len[r] > 0 ? a.len[r] : 1) + 63) & ~63) >> 5) - 1;
+        double mean, window;
+        if (len <= ws) {                                           // read.cpp:217-218
+            const int hits = kw_popcount(m, S, len, last_word, lane);
+            mean = 100.0 * (double)hits / (double)len;             // read.cpp:208-213 (0/0 = NaN for an empty read, as there)
+            window = mean;
+        } else {
+            int c = kw_popcount(m, S, ws, last_word, lane);        // read.cpp:220-222: the first window's sum is an exact integer
+            const int c0 = c;
+            int hits = 0;                                          // ones entering the window, per lane
+            double best = (double)c / wsd;                         // read.cpp:223
+            KwAnchor an;
+            kw_set_anchor(an, k, best, c);
+            int cmin = c, trec = c;                                // lowest / highest after-step count of the current epoch
+            const int T = len - ws;                                // steps: base S + ws + t enters, base S + t leaves
+            for (int t0 = 0; t0 < T; t0 += 1024) {
+                const int tl = t0 + 32 * (int)lane;
+                const int nv = T - tl;
+                uint32_t in = 0, out = 0;
+                if (nv > 0) {
+                    in = kw_bits(m, (long long)S + ws + tl, last_word);
+                    out = kw_bits(m, (long long)S + tl, last_word);
+                    if (nv < 32) {
+                        const uint32_t vm = (1u << nv) - 1u;
+                        in &= vm;
+                        out &= vm;
+                    }
+                }
+                hits += __popc(in);
+                const uint32_t pin = in & ~out, pout = out & ~in, both = in & out;
+                int delta = 0, mn = 99, mx = -99;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const unsigned e = lut[((pin >> (4 * q)) & 15u) | (((pout >> (4 * q)) & 15u) << 4)];
+                    const int lo_q = delta + (int)((e >> 4) & 15u) - 4, hi_q = delta + (int)((e >> 8) & 15u) - 4;
+                    mn = lo_q < mn ? lo_q : mn;
+                    mx = hi_q > mx ? hi_q : mx;
+                    delta += (int)(e & 15u) - 4;
+                }
+                int incl = delta;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (unsigned)d) incl += t;
+                }
+                const int cs = c + incl - delta;                   // count at the start of this lane's word
+                const bool valid = nv > 0;
+                const int mn0 = mn < 0 ? mn : 0, mx0 = mx > 0 ? mx : 0;
+                // levels the word visits, including the dip of a step that subtracts and adds in the same step
+                const int lo_level = cs + mn0 - (both ? 1 : 0), hi_level = cs + mx0;
+                bool tz = false;
+                for (int i = 0; i < k.n_zones; ++i) tz |= lo_level <= k.zhi[i] && hi_level >= k.zlo[i];
+                int emax = -0x7FFFFFFF;                            // top of the highest edge interval that starts at or below hi_level
+                for (int i = 0; i < k.n_edges; ++i)
+                    if (k.elo[i] <= hi_level && k.ehi[i] > emax) emax = k.ehi[i];
+                int cur = 0;
+                for (;;) {
+                    const bool in_range = valid && (int)lane >= cur;
+                    const bool flag = in_range && (tz || (hi_level > trec && (hi_level > an.c_edge || emax >= trec)));
+                    const unsigned fm = __ballot_sync(0xffffffffu, flag);
+                    const int first = fm ? __ffs(fm) - 1 : 32;
+                    const bool seg = in_range && (int)lane < first;
+                    const int seg_min = __reduce_min_sync(0xffffffffu, seg ? cs + mn : 0x7FFFFFFF);
+                    const int seg_max = __reduce_max_sync(0xffffffffu, seg ? hi_level : -0x7FFFFFFF);
+                    cmin = seg_min < cmin ? seg_min : cmin;
+                    trec = seg_max > trec ? seg_max : trec;
+                    if (first == 32) break;
+                    // close the epoch, then walk the flagged word with the reference's own operations
+                    const double f = kw_eval(an, k, cmin);
+                    best = f < best ? f : best;
+                    int cw = __shfl_sync(0xffffffffu, cs, first);
+                    const uint32_t win = __shfl_sync(0xffffffffu, in, first), wout = __shfl_sync(0xffffffffu, out, first);
+                    double w = kw_eval(an, k, cw);
+                    uint32_t todo = win | wout;
+                    while (todo) {
+                        const int t = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        if ((wout >> t) & 1u) { w -= k.rq; --cw; }     // read.cpp:229 (w -= 0.0 changes nothing)
+                        if ((win >> t) & 1u) { w += k.rq; ++cw; }      // read.cpp:230
+                        best = w < best ? w : best;                    // read.cpp:231-232
+                    }
+                    kw_set_anchor(an, k, w, cw);
+                    cmin = cw;
+                    trec = cw;
+                    cur = first + 1;
+                }
+                c += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            {
+                const double f = kw_eval(an, k, cmin);
+                best = f < best ? f : best;
+            }
+            if (best < 0.5 / wsd) best = 0.0;                      // read.cpp:233-234
+            hits = __reduce_add_sync(0xffffffffu, hits) + c0;
+            mean = 100.0 * (double)hits / (double)len;             // read.cpp:208-213
+            window = 100.0 * best;
+        }
+        if (lane == 0) {
+            const uint8_t passed = fl_hard_cutoffs(a.p, len, mean, window);        // read.cpp:65-73
+            if (is_read) {
+                a.r_mean[r] = mean;
+                a.r_window[r] = window;
+                a.r_passed[r] = passed;
+            }
+            if (row >= 0) {
+                a.w_mean[row] = mean;
+                a.w_window[row] = window;
+                a.w_passed[row] = passed;
+            }
+        }
+    }
 }
 
 __global__ void k_identity_rows(uint32_t n, const int32_t *__restrict__ len, uint32_t *w_parent, int32_t *w_start,
@@ -566,6 +763,43 @@ int fl_reserve_rows(fl_ctx *c, size_t n_total) {
     return FL_OK;
 }
 
+// the window-size dependent constants of k_kmer_window (mirrors kw_consts of tests/models/kmer_window_model.c)
+static void kw_make_consts(int ws, KwConsts *k) {
+    memset(k, 0, sizeof(*k));
+    k->rq = 1.0 / (double)ws;                                       // read.cpp:229-230: qualities[i] / window_size with q == 1.0
+    long long b;
+    memcpy(&b, &k->rq, 8);
+    k->e_rq = (int)((b >> 52) & 0x7FF) - 1023;
+    k->mant_rq = ((unsigned long long)b & ((1ull << 52) - 1ull)) | (1ull << 52);
+    for (int e = k->e_rq; e <= 1 && k->n_edges < KW_MAX_EDGES; ++e) {     // edges 2^e of every binade a count 0..ws can reach
+        const double x = ldexp(1.0, e) * (double)ws;
+        if (x > (double)ws + 3.0) break;
+        k->elo[k->n_edges] = (int)floor(x) - 2;
+        k->ehi[k->n_edges] = (int)ceil(x) + 2;
+        k->n_edges++;
+    }
+    for (int s = 1; s <= 52 && k->e_rq + s <= 1; ++s) {
+        if ((k->mant_rq & ((1ull << s) - 1ull)) != (1ull << (s - 1))) continue;
+        // tie binade [2^e, 2^(e+1)), e = e_rq + s: levels c with c * rq inside it, +- 1e-9 relative for the chain's
+        // drift, +- one level so that every operation with an end inside the binade lies inside the zone
+        const double lo = ldexp(1.0, k->e_rq + s), hi = ldexp(1.0, k->e_rq + s + 1);
+        int zl = (int)floor(lo * (1.0 - 1e-9) * (double)ws) - 1;
+        const int zh = (int)ceil(hi * (1.0 + 1e-9) * (double)ws) + 1;
+        if (zl < 0) zl = 0;
+        if (zl > ws) continue;
+        if (k->n_zones < KW_MAX_ZONES) {
+            k->zlo[k->n_zones] = zl;
+            k->zhi[k->n_zones] = zh;
+            k->n_zones++;
+        } else {                                                    // too many: one zone covering everything (every word is walked)
+            k->n_zones = 1;
+            k->zlo[0] = 0;
+            k->zhi[0] = 0x7FFFFFFF;
+            return;
+        }
+    }
+}
+
 static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     if (!b.seq2b) { ctx->set_error("k-mer scoring needs seq2b"); return FL_EINVAL; }
     const size_t n = b.n;
@@ -578,17 +812,17 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     ctx->launches++;
     FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64a.p, ctx->sc_u64a.p, n, ctx->d_scalars));
     FL_CUDA(ctx, cudaMemcpyAsync(ctx->sc_u64a.p + n, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    FL_CUDA(ctx, cudaStreamSynchronize(st));
-    const unsigned long long n_tiles = ctx->h_scalars[0];
-    if (n_tiles) {
+    {
         ProbeArgs pa{};
         pa.seq2b = b.seq2b; pa.off = b.off; pa.len = b.len; pa.tile_start = ctx->sc_u64a.p;
-        pa.n = b.n; pa.n_tiles = n_tiles; pa.bitmap = ctx->d_bitmap; pa.anchor = ctx->d_anchor; pa.mask = ctx->sc_mask.p;
+        pa.n = b.n; pa.bitmap = ctx->d_bitmap; pa.anchor = ctx->d_anchor; pa.mask = ctx->sc_mask.p;
         pa.filter = ctx->d_filter; pa.filter_log2_words = ctx->filter_log2_words; pa.filter_kind = ctx->filter_kind;
-        unsigned blocks = (unsigned)((n_tiles + 7) / 8);
+        // persistent grid; the kernel reads the tile count from tile_start[n], so nothing here waits for the scan
+        unsigned long long tiles_bound = (b.padded_bases + FL_TILE_BASES - 1) / FL_TILE_BASES + n;
+        unsigned blocks = (unsigned)((tiles_bound + 7) / 8);
         unsigned max_blocks = (unsigned)ctx->sm_count * 4;
         if (blocks > max_blocks) blocks = max_blocks;
+        if (blocks < 1) blocks = 1;
         {
             KernelTimer kt(ctx, FL_KERNEL_PROBE_PAINT);
             // keep the pre-filter resident in the L2 set-aside while the probe kernel streams reads past it
@@ -603,23 +837,16 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
             }
+            const bool mini = (ctx->filter_kind & 1) != 0;      // minimizer-keyed filter words, loads de-duplicated per lane
             if (ctx->use_anchor) {
-                if (ctx->use_filter) k_probe_paint<2, true, true><<<blocks, 256, 0, st>>>(pa);
-                else k_probe_paint<2, false, true><<<blocks, 256, 0, st>>>(pa);
-            } else if (ctx->use_filter) {
-                switch (ctx->probe_mode) {
-                    case 0: k_probe_paint<0, true, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 2: k_probe_paint<2, true, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 3: k_probe_paint<3, true, false><<<blocks, 256, 0, st>>>(pa); break;
-                    default: k_probe_paint<1, true, false><<<blocks, 256, 0, st>>>(pa); break;
-                }
+                if (ctx->use_filter && mini) k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa);
+                else if (ctx->use_filter) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
+                else k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
+            } else if (ctx->use_filter) {                        // plain bitmap (FL_ANCHOR=0: cross-checks and profiling)
+                if (mini) k_probe_paint<2, 2, false><<<blocks, 256, 0, st>>>(pa);
+                else k_probe_paint<2, 1, false><<<blocks, 256, 0, st>>>(pa);
             } else {
-                switch (ctx->probe_mode) {
-                    case 0: k_probe_paint<0, false, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 2: k_probe_paint<2, false, false><<<blocks, 256, 0, st>>>(pa); break;
-                    case 3: k_probe_paint<3, false, false><<<blocks, 256, 0, st>>>(pa); break;
-                    default: k_probe_paint<1, false, false><<<blocks, 256, 0, st>>>(pa); break;
-                }
+                k_probe_paint<2, 0, false><<<blocks, 256, 0, st>>>(pa);
             }
             if (persist) {
                 cudaStreamAttrValue attr{};
@@ -630,46 +857,22 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
     }
-    // ---- B1: ranges ----
+    // ---- B: first / last, bad ranges, children (k_kmer_scan), then mean + window quality per item (k_kmer_window) ----
     const size_t rb = ctx->n_reads, wb = ctx->n_rows;
-    FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, st));
-    KmerArgs ka{};
-    ka.mask = ctx->sc_mask.p; ka.off = b.off; ka.len = b.len; ka.n = b.n; ka.p = ctx->p;
-    ka.r_len = ctx->r_len.p + rb; ka.r_first = ctx->r_first.p + rb; ka.r_last = ctx->r_last.p + rb;
-    ka.r_nbad = ctx->r_nbad.p + rb; ka.r_nchild = ctx->r_nchild.p + rb;
-    ka.r_mean = ctx->r_mean.p + rb; ka.r_window = ctx->r_window.p + rb; ka.r_passed = ctx->r_passed.p + rb;
-    ka.r_rowstart = ctx->r_rowstart.p + rb; ka.rows_per_read = ctx->sc_u64b.p;
-    ka.read_base = rb; ka.row_base = wb;
-    k_kmer_ranges<<<fl_blocks(n, 256), 256, 0, st>>>(ka);
-    ctx->launches++;
-    // ---- B3 on the parents (their own raw mean / window / passed: read.cpp:60-73) ----
-    FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
-    FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
-    FL_CUDA(ctx, ctx->sc_u32a.reserve(n, 0, st));
-    k_iota<<<fl_blocks(n, 256), 256, 0, st>>>(ctx->sc_u32a.p, b.n, (uint32_t)rb);   // parent of "row" i is read rb + i
-    ctx->launches++;
-    const unsigned stat_blocks_max = (unsigned)ctx->sm_count * 8;
-    {
-        StatArgs sa{};
-        sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.order = ctx->sc_order.p; sa.n_rows = b.n; sa.p = ctx->p;
-        sa.w_parent = ctx->sc_u32a.p;
-        // whole-read ranges: start 0, end len -> reuse r_len as "end" and a zero array for start
-        FL_CUDA(ctx, ctx->sc_u64c.reserve((n + 1) / 2 + 1, 0, st));
-        int32_t *zeros = reinterpret_cast<int32_t *>(ctx->sc_u64c.p);
-        FL_CUDA(ctx, cudaMemsetAsync(zeros, 0, n * sizeof(int32_t), st));
-        sa.w_start = zeros; sa.w_end = b.len;
-        sa.w_mean = ctx->r_mean.p + rb; sa.w_window = ctx->r_window.p + rb; sa.w_passed = ctx->r_passed.p + rb;
-        sa.read_base = rb;
-        unsigned blocks = fl_blocks(n, 256);
-        if (blocks > stat_blocks_max) blocks = stat_blocks_max;
-        {
-            KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
-            k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
-        }
-        ctx->launches++;
-    }
-    // ---- rows ----
     const bool may_have_children = ctx->p.trim || ctx->p.split_set;
+    FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, st));
+    FL_CUDA(ctx, ctx->sc_items.reserve(n + 8, 0, st));
+    ScanArgs sa{};
+    sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.len = b.len; sa.n = b.n; sa.p = ctx->p;
+    sa.r_len = ctx->r_len.p + rb; sa.r_first = ctx->r_first.p + rb; sa.r_last = ctx->r_last.p + rb;
+    sa.r_nbad = ctx->r_nbad.p + rb; sa.r_nchild = ctx->r_nchild.p + rb;
+    sa.r_rowstart = ctx->r_rowstart.p + rb; sa.rows_per_read = ctx->sc_u64b.p;
+    sa.item_len = ctx->sc_items.p;
+    sa.read_base = rb; sa.row_base = wb;
+    unsigned scan_blocks = fl_blocks(n * 32, 256);
+    if (scan_blocks > (unsigned)ctx->sm_count * 8) scan_blocks = (unsigned)ctx->sm_count * 8;
+    k_kmer_scan<false><<<scan_blocks, 256, 0, st>>>(sa);
+    ctx->launches++;
     size_t n_rows_batch = n;
     if (may_have_children) {
         FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64b.p, ctx->r_rowstart.p + rb, n, ctx->d_scalars));
@@ -678,38 +881,39 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         n_rows_batch = (size_t)ctx->h_scalars[0];
     }
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n_rows_batch));
+    size_t n_items = n;
     if (!may_have_children) {
         k_identity_rows<<<fl_blocks(n, 256), 256, 0, st>>>(b.n, b.len, ctx->w_parent.p + wb, ctx->w_start.p + wb,
                                                           ctx->w_end.p + wb, rb);
         ctx->launches++;
-        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_mean.p + wb, ctx->r_mean.p + rb, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_window.p + wb, ctx->r_window.p + rb, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        FL_CUDA(ctx, cudaMemcpyAsync(ctx->w_passed.p + wb, ctx->r_passed.p + rb, n, cudaMemcpyDeviceToDevice, st));
     } else {
-        RowArgs ra{};
-        ra.mask = ctx->sc_mask.p; ra.off = b.off; ra.len = b.len; ra.n = b.n; ra.p = ctx->p;
-        ra.r_first = ctx->r_first.p + rb; ra.r_last = ctx->r_last.p + rb; ra.r_nchild = ctx->r_nchild.p + rb;
-        ra.r_rowstart = ctx->r_rowstart.p + rb;
-        ra.w_parent = ctx->w_parent.p + wb; ra.w_start = ctx->w_start.p + wb; ra.w_end = ctx->w_end.p + wb;
-        FL_CUDA(ctx, ctx->sc_u64c.reserve((n_rows_batch + 1) / 2 + 1, 0, st));
-        ra.w_len = reinterpret_cast<int32_t *>(ctx->sc_u64c.p);
-        ra.read_base = rb; ra.row_base = wb;
-        k_kmer_rows<<<fl_blocks(n, 256), 256, 0, st>>>(ra);
-        ctx->launches++;
-        FL_CUDA(ctx, ctx->sc_order.reserve(n_rows_batch, 0, st));
-        FL_TRY(fl_order_by_length(ctx, ra.w_len, n_rows_batch, ctx->sc_order.p));
-        StatArgs sa{};
-        sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.order = ctx->sc_order.p; sa.n_rows = (uint32_t)n_rows_batch; sa.p = ctx->p;
+        n_items = n + n_rows_batch;
+        FL_CUDA(ctx, ctx->sc_items.reserve(n_items + 8, n, st));
+        sa.item_len = ctx->sc_items.p;
         sa.w_parent = ctx->w_parent.p + wb; sa.w_start = ctx->w_start.p + wb; sa.w_end = ctx->w_end.p + wb;
-        sa.w_mean = ctx->w_mean.p + wb; sa.w_window = ctx->w_window.p + wb; sa.w_passed = ctx->w_passed.p + wb;
-        sa.read_base = rb;
-        sa.r_nchild = ctx->r_nchild.p + rb; sa.r_mean = ctx->r_mean.p + rb; sa.r_window = ctx->r_window.p + rb;
-        sa.r_passed = ctx->r_passed.p + rb;
-        unsigned blocks = fl_blocks(n_rows_batch, 256);
-        if (blocks > stat_blocks_max) blocks = stat_blocks_max;
+        k_kmer_scan<true><<<scan_blocks, 256, 0, st>>>(sa);
+        ctx->launches++;
+    }
+    FL_CUDA(ctx, ctx->sc_order.reserve(n_items, 0, st));
+    FL_TRY(fl_order_by_length(ctx, ctx->sc_items.p, n_items, ctx->sc_order.p));
+    {
+        WinArgs wa{};
+        wa.mask = ctx->sc_mask.p; wa.off = b.off; wa.len = b.len; wa.order = ctx->sc_order.p;
+        wa.n_items = (uint32_t)n_items; wa.n_reads = b.n; wa.p = ctx->p;
+        kw_make_consts(ctx->p.window_size, &wa.k);
+        wa.r_nchild = ctx->r_nchild.p + rb; wa.r_rowstart = ctx->r_rowstart.p + rb;
+        wa.row_base = wb; wa.read_base = rb;
+        wa.w_parent = ctx->w_parent.p + wb; wa.w_start = ctx->w_start.p + wb; wa.w_end = ctx->w_end.p + wb;
+        wa.r_mean = ctx->r_mean.p + rb; wa.r_window = ctx->r_window.p + rb; wa.r_passed = ctx->r_passed.p + rb;
+        wa.w_mean = ctx->w_mean.p + wb; wa.w_window = ctx->w_window.p + wb; wa.w_passed = ctx->w_passed.p + wb;
+        wa.work = ctx->d_scalars + 26;
+        FL_CUDA(ctx, cudaMemsetAsync(wa.work, 0, sizeof(unsigned long long), st));
+        unsigned blocks = fl_blocks(n_items * 32, 256);
+        const unsigned cap = (unsigned)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
         {
             KernelTimer kt(ctx, FL_KERNEL_KMER_STATS);
-            k_kmer_stats<<<blocks, 256, 0, st>>>(sa);
+            k_kmer_window<<<blocks, 256, 0, st>>>(wa);
         }
         ctx->launches++;
     }

@@ -1,0 +1,272 @@
+/* tests/models/kmer_window_model.c -- TEST INFRASTRUCTURE: a scalar CPU model of the device algorithm of
+ * k_kmer_window (filtlong_b200/csrc/fl_score.cu), which computes the k-mer-mode window quality of
+ * read.cpp:216-236 bit for bit WITHOUT walking a row base by base.
+ *
+ * The reference's recurrence on qualities in {0, 1}:   w -= out ? rq : 0;  w += in ? rq : 0;  best = min(best, w)
+ * with rq = fl(1 / ws), started from w0 = fl(c0 / ws). Let c be the window's hit count (an integer prefix
+ * sum of the mask: parallel). Facts used (IEEE-754 round to nearest even; "grid" of a binade = its ulp):
+ *
+ *  (1) inside one binade whose grid does not put rq exactly half way between two grid points ("tie binade"),
+ *      adding / subtracting rq moves w by exactly R = rq rounded to the grid: the two are inverse;
+ *  (2) subtracting rq across a binade edge (the lower grid is finer, w is on it) and adding it back returns
+ *      to the same value (the two roundings compose to the identity whatever the parity: see DESIGN.md);
+ *  (3) so, starting from an ANCHOR (w_a, c_a), every value the chain takes at a level c that is reached by
+ *      moves BELOW the anchor's binade ceiling, and outside tie binades, is one fixed function F(c): the
+ *      value obtained by walking from the anchor down (or up, inside the anchor's binade) to c. The chain's
+ *      minimum over such a stretch ("epoch") is F(min c) -- one count reduction and one short walk;
+ *  (4) what is NOT reversible: an addition that takes the chain to a level it has not visited since the anchor
+ *      AND sits next to a binade edge -- it either carries w into the coarser grid above (which forgets the
+ *      low bit) or leaves the binade's lowest level (the subtraction that would undo it falls through the
+ *      floor onto the finer grid); a new epoch starts from the value it produced. And anything inside a tie
+ *      binade (rounding depends on the parity of w). Words of 32 steps whose count range does either are
+ *      walked with true double operations; they are rare (a handful of record levels per row; for ws = 250
+ *      the only tie binade is [2^-5, 2^-4): windows with 8..15 hits).
+ *
+ * The model processes a row in words of 32 steps exactly like one lane of the kernel does (word statistics
+ * from a nibble look-up table, a predicate that flags the word, a scalar walk only if flagged), so that the
+ * CUDA code is a transcription of this file.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define KW_MAX_ZONES 8
+
+typedef struct {
+    double rq;
+    int e_rq;             /* rq in [2^e_rq, 2^(e_rq+1)) */
+    uint64_t mant_rq;     /* 53-bit significand of rq */
+    int n_zones;          /* count intervals [zlo, zhi] whose values may lie in a tie binade (one level of margin) */
+    int zlo[KW_MAX_ZONES], zhi[KW_MAX_ZONES];
+    int n_edges;          /* count intervals around the binade edges 2^e / rq (two levels of margin) */
+    int elo[16], ehi[16];
+} chain_consts;
+
+typedef struct {
+    double w;             /* anchor value */
+    int c;                /* anchor count */
+    int lattice;          /* anchor's binade has a usable grid (above rq's own binade, not a tie binade) */
+    int64_t wb, rint, lo, hi;
+    int c_edge;           /* highest level reachable from the anchor without leaving its binade upwards (conservative) */
+} anchor_t;
+
+static inline int64_t d2b(double x) { int64_t b; memcpy(&b, &x, 8); return b; }
+static inline double b2d(int64_t b) { double x; memcpy(&x, &b, 8); return x; }
+
+void kw_consts(chain_consts *k, int ws) {
+    k->rq = 1.0 / (double)ws;
+    const int64_t b = d2b(k->rq);
+    k->e_rq = (int)((b >> 52) & 0x7FF) - 1023;
+    k->mant_rq = ((uint64_t)b & ((1ull << 52) - 1ull)) | (1ull << 52);
+    k->n_zones = 0;
+    k->n_edges = 0;
+    for (int e = k->e_rq; e <= 1 && k->n_edges < 16; ++e) {           /* edges 2^e for every binade a count 0..ws can reach */
+        const double x = ldexp(1.0, e) * (double)ws;
+        if (x > (double)ws + 3.0) break;
+        k->elo[k->n_edges] = (int)floor(x) - 2;
+        k->ehi[k->n_edges] = (int)ceil(x) + 2;
+        k->n_edges++;
+    }
+    for (int s = 1; s <= 52 && k->e_rq + s <= 1; ++s) {
+        if ((k->mant_rq & ((1ull << s) - 1ull)) != (1ull << (s - 1))) continue;
+        /* tie binade [2^e, 2^(e+1)), e = e_rq + s: levels c with c * rq within it, +- a relative 1e-9 for the
+         * drift of the chain, +- one level so that every operation with an end inside the binade is inside the zone */
+        const double lo = ldexp(1.0, k->e_rq + s), hi = ldexp(1.0, k->e_rq + s + 1);
+        int zl = (int)floor(lo * (1.0 - 1e-9) * (double)ws) - 1, zh = (int)ceil(hi * (1.0 + 1e-9) * (double)ws) + 1;
+        if (zl < 0) zl = 0;
+        if (zl > ws) continue;
+        if (k->n_zones < KW_MAX_ZONES) {
+            k->zlo[k->n_zones] = zl;
+            k->zhi[k->n_zones] = zh;
+            k->n_zones++;
+        } else {                      /* too many: one zone covering everything (every word walks) */
+            k->n_zones = 1; k->zlo[0] = 0; k->zhi[0] = 0x7FFFFFFF;
+            return;
+        }
+    }
+}
+
+static inline int touches_zone(const chain_consts *k, int lo, int hi) {
+    for (int i = 0; i < k->n_zones; ++i)
+        if (lo <= k->zhi[i] && hi >= k->zlo[i]) return 1;
+    return 0;
+}
+
+static inline int touches_edge(const chain_consts *k, int lo, int hi) {
+    for (int i = 0; i < k->n_edges; ++i)
+        if (lo <= k->ehi[i] && hi >= k->elo[i]) return 1;
+    return 0;
+}
+
+/* grid parameters of the binade of w; returns 0 if it has none (rq's own binade and below: arithmetic there is exact) */
+static int binade_of(const chain_consts *k, double w, int64_t *wb, int64_t *rint, int64_t *lo, int64_t *hi) {
+    if (!(w > 0.0)) return 0;
+    const int64_t b = d2b(w);
+    const int e = (int)((b >> 52) & 0x7FF) - 1023;
+    const int s = e - k->e_rq;
+    if (s < 1 || s > 52) return 0;
+    const uint64_t half = 1ull << (s - 1);
+    if ((k->mant_rq & ((1ull << s) - 1ull)) == half) return 0;      /* tie binade (only met inside a zone) */
+    *wb = b;
+    *rint = (int64_t)((k->mant_rq + half) >> s);
+    *lo = (int64_t)(e + 1023) << 52;
+    *hi = *lo + (1ll << 52);
+    return 1;
+}
+
+static void set_anchor(anchor_t *a, const chain_consts *k, double w, int c) {
+    a->w = w;
+    a->c = c;
+    a->lattice = binade_of(k, w, &a->wb, &a->rint, &a->lo, &a->hi);
+    a->c_edge = c;                                                   /* no usable grid: any level above the anchor ends the epoch */
+    if (a->lattice) a->c_edge = c + (int)((a->hi - 2 - a->wb) / a->rint);
+}
+
+/* F(c) for c <= a->c_edge: the chain's value at level c inside the anchor's epoch */
+static double eval_F(const anchor_t *a, const chain_consts *k, int c, long long *n_true_ops) {
+    if (c >= a->c) return a->lattice ? b2d(a->wb + a->rint * (int64_t)(c - a->c)) : a->w;   /* (c > a->c only with a grid) */
+    double w = a->w;
+    int cur = a->c;
+    while (cur > c) {                                                /* walk down: grid jumps inside a binade, true subtractions at its floor */
+        int64_t wb, rint, lo, hi;
+        if (binade_of(k, w, &wb, &rint, &lo, &hi)) {
+            int64_t room = (wb - (lo + 1)) / rint;                   /* levels that can be descended while staying >= lo + 1 */
+            if (room > (int64_t)(cur - c)) room = cur - c;
+            if (room > 0) {
+                w = b2d(wb - rint * room);
+                cur -= (int)room;
+                continue;
+            }
+        }
+        w = w - k->rq;                                               /* read.cpp:229 */
+        ++*n_true_ops;
+        --cur;
+    }
+    return w;
+}
+
+/* nibble table: for 4 steps with pure-plus bits p and pure-minus bits m (p & m == 0): packed
+ * (delta + 4) | (min_after + 4) << 4 | (max_after + 4) << 8, min / max over the after-step partial sums */
+static uint16_t g_lut[256];
+static int g_lut_ready = 0;
+static void build_lut(void) {
+    for (int p = 0; p < 16; ++p)
+        for (int m = 0; m < 16; ++m) {
+            int d = 0, mn = 99, mx = -99;
+            for (int t = 0; t < 4; ++t) {
+                d += ((p >> t) & 1) - ((m >> t) & 1);
+                if (d < mn) mn = d;
+                if (d > mx) mx = d;
+            }
+            g_lut[p | (m << 4)] = (uint16_t)((d + 4) | ((mn + 4) << 4) | ((mx + 4) << 8));
+        }
+    g_lut_ready = 1;
+}
+
+static void word_stats(uint32_t pin, uint32_t pout, int *delta, int *mn, int *mx) {
+    int d = 0, lo = 99, hi = -99;
+    for (int k = 0; k < 8; ++k) {
+        const unsigned e = g_lut[((pin >> (4 * k)) & 15u) | (((pout >> (4 * k)) & 15u) << 4)];
+        const int dd = (int)(e & 15u) - 4, m0 = (int)((e >> 4) & 15u) - 4, m1 = (int)((e >> 8) & 15u) - 4;
+        if (d + m0 < lo) lo = d + m0;
+        if (d + m1 > hi) hi = d + m1;
+        d += dd;
+    }
+    *delta = d; *mn = lo; *mx = hi;
+}
+
+/* window quality (already x 100) of the row [S, E) of a hit mask (bit i of mask[i >> 5] = base i covered) */
+double kmer_window_model(const uint32_t *mask, int S, int E, int ws, long long *n_true_ops_out, long long *n_slow_words_out) {
+    if (!g_lut_ready) build_lut();
+    const int len = E - S;
+    long long n_true = 0, n_slow = 0;
+#define BIT(i) ((mask[(i) >> 5] >> ((i) & 31)) & 1u)
+    if (len <= ws) {                                                   /* read.cpp:217-218 */
+        long long hits = 0;
+        for (int i = S; i < E; ++i) hits += BIT(i);
+        if (n_true_ops_out) *n_true_ops_out = 0;
+        if (n_slow_words_out) *n_slow_words_out = 0;
+        return 100.0 * (double)hits / (double)len;
+    }
+    chain_consts k;
+    kw_consts(&k, ws);
+    int c = 0;
+    for (int i = S; i < S + ws; ++i) c += BIT(i);
+    double best = (double)c / (double)ws;                              /* read.cpp:220-223 */
+    anchor_t a;
+    set_anchor(&a, &k, best, c);
+    int cmin = c;                                                      /* lowest after-step count of the current epoch */
+    int trec = c;                                                      /* highest level visited since the anchor */
+    const int T = len - ws;                                            /* steps: in = base S+ws+t, out = base S+t */
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        uint32_t in = 0, out = 0;
+        const int nv = T - t0 < 32 ? T - t0 : 32;
+        for (int j = 0; j < nv; ++j) {
+            in |= BIT(S + ws + t0 + j) << j;
+            out |= BIT(S + t0 + j) << j;
+        }
+        const uint32_t pin = in & ~out, pout = out & ~in, both = in & out;
+        int delta, mn, mx;
+        word_stats(pin, pout, &delta, &mn, &mx);
+        const int mn0 = mn < 0 ? mn : 0, mx0 = mx > 0 ? mx : 0;
+        /* levels the word visits, including the dip of a step that subtracts and adds in the same step */
+        const int lo_level = c + mn0 - (both ? 1 : 0), hi_level = c + mx0;
+        const int flagged = touches_zone(&k, lo_level, hi_level) ||
+                            (hi_level > trec && (hi_level > a.c_edge || touches_edge(&k, trec, hi_level)));
+        if (!flagged) {
+            if (c + mn < cmin) cmin = c + mn;
+            if (hi_level > trec) trec = hi_level;
+            c += delta;
+            continue;
+        }
+        ++n_slow;
+        {   /* close the epoch, then walk the word with the reference's own operations */
+            const double f = eval_F(&a, &k, cmin, &n_true);
+            if (f < best) best = f;
+        }
+        double w = eval_F(&a, &k, c, &n_true);
+        uint32_t todo = in | out;
+        while (todo) {
+            const int t = __builtin_ctz(todo);
+            todo &= todo - 1;
+            if ((out >> t) & 1) { w -= k.rq; --c; ++n_true; }          /* read.cpp:229 (w -= 0.0 changes nothing) */
+            if ((in >> t) & 1) { w += k.rq; ++c; ++n_true; }           /* read.cpp:230 */
+            if (w < best) best = w;
+        }
+        set_anchor(&a, &k, w, c);
+        cmin = c;
+        trec = c;
+    }
+    {
+        const double f = eval_F(&a, &k, cmin, &n_true);
+        if (f < best) best = f;
+    }
+#undef BIT
+    if (best < 0.5 / (double)ws) best = 0.0;                           /* read.cpp:233-234 */
+    if (n_true_ops_out) *n_true_ops_out = n_true;
+    if (n_slow_words_out) *n_slow_words_out = n_slow;
+    return 100.0 * best;
+}
+
+/* the reference recurrence itself (read.cpp:216-236 on {0, 1} qualities), for the comparison */
+double kmer_window_reference(const uint32_t *mask, int S, int E, int ws) {
+#define BIT(i) ((mask[(i) >> 5] >> ((i) & 31)) & 1u)
+    const int len = E - S;
+    if (len <= ws) {
+        long long hits = 0;
+        for (int i = S; i < E; ++i) hits += BIT(i);
+        return 100.0 * (double)hits / (double)len;
+    }
+    double sum = 0.0;
+    for (int i = S; i < S + ws; ++i) sum += BIT(i) ? 1.0 : 0.0;
+    double w = sum / (double)ws, best = w;
+    for (int t = 0; t < len - ws; ++t) {
+        const double qo = BIT(S + t) ? 1.0 : 0.0, qi = BIT(S + ws + t) ? 1.0 : 0.0;
+        w -= qo / (double)ws;
+        w += qi / (double)ws;
+        if (w < best) best = w;
+    }
+    if (best < 0.5 / (double)ws) best = 0.0;
+    return 100.0 * best;
+#undef BIT
+}

@@ -192,6 +192,29 @@ def test_kmer_assembly_random(seed, opts):
     ctx.close()
 
 
+@pytest.mark.parametrize("ws", [17, 100, 250, 256, 333, 470, 1000])
+def test_kmer_window_kernel_window_sizes_and_long_rows(ws):
+    """k_kmer_window on rows from a few bases to > 100 kbases (many 1024-step iterations per warp), clean and
+    junk-ridden, for window sizes with different tie binades: every raw mean / window quality bit-exact."""
+    rng = np.random.default_rng(1000 + ws)
+    genome = util.rand_seq(rng, 300000)
+    reads = []
+    for i in range(60):
+        L = int([50, ws, ws + 1, 2000, 20000, 120000][i % 6] * rng.uniform(0.9, 1.1))
+        s = int(rng.integers(0, len(genome) - L))
+        seq = util.mutate(rng, genome[s:s + L], [0.0, 0.03, 0.08, 0.12, 0.16][i % 5])
+        if i % 4 == 1 and L > 3000:
+            cut = int(rng.integers(500, L - 500))
+            seq = seq[:cut] + util.rand_seq(rng, int(rng.integers(200, 2500))) + seq[cut:]
+        if i % 7 == 3:
+            seq = util.rand_seq(rng, int(rng.integers(1, 90))) + seq + util.rand_seq(rng, int(rng.integers(1, 90)))
+        reads.append((seq, b"I" * len(seq)))
+    for opts in (dict(keep_percent=80.0, window_size=ws), dict(keep_percent=80.0, window_size=ws, trim=True, split=400, min_window_q=40.0)):
+        ctx, summ, sc, ok = run_both(reads, opts, assembly=[genome])
+        full_check(ctx, summ, sc)
+        ctx.close()
+
+
 @pytest.mark.parametrize("seed,opts", [(21, dict(keep_percent=85.0, trim=True, split=120)),
                                        (22, dict(target_bases=200000))])
 def test_kmer_short_reads_random(seed, opts):
