@@ -9,6 +9,12 @@ for kind in 3 2; do
   tail -3 gpurun_out/bench_k${kind}.err
 done
 timeout 900 python bench.py --steps 10 --warmup 3 --configs c5 --no-cpu-baseline > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err
+for pm in 1 2; do
+  FL_PHRED_MODE=$pm timeout 600 python bench.py --steps 20 --warmup 3 --configs c2 --no-cpu-baseline --no-e2e > gpurun_out/bench_c2_pm${pm}.json 2> gpurun_out/bench_c2_pm${pm}.err
+  tail -2 gpurun_out/bench_c2_pm${pm}.err
+  python -c "
+import json;d=json.loads(open('gpurun_out/bench_c2_pm${pm}.json').read().strip().splitlines()[-1]);print('c2 phred_mode ${pm}', d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['result'])"
+done
 python - <<'PY'
 import json
 for f in ("bench_k3","bench_k2","bench_c5"):
