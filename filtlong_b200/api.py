@@ -180,6 +180,25 @@ class Context:
         b = host_batch.c_batch()
         self._ck(self.L.fl_reads_push(self.h, C.byref(b)), "fl_reads_push")
 
+    def push_text(self, data: bytes, fastq=True, is_last=True, cap=None):
+        """fl_reads_push_text on one chunk of FASTQ / FASTA text. Returns a dict with status, n, consumed and
+        the record index arrays (chunk-relative offsets)."""
+        n_cap = cap if cap is not None else max(data.count(b"\n") // (4 if fastq else 2) + 2, 8)
+        arr = dict(name_off=np.zeros(n_cap, np.uint64), name_len=np.zeros(n_cap, np.uint32), comment_len=np.zeros(n_cap, np.uint32),
+                   seq_off=np.zeros(n_cap, np.uint64), qual_off=np.zeros(n_cap, np.uint64), len=np.zeros(n_cap, np.int32),
+                   name_hash=np.zeros(n_cap, np.uint64))
+        rec = capi.TextRecords(cap=n_cap, **{k: capi.ptr(v) for k, v in arr.items()})
+        n, used, st = C.c_uint64(), C.c_uint64(), C.c_int()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        rc = self.L.fl_reads_push_text(self.h, capi.ptr(buf), len(data), 1 if fastq else 2, int(is_last), C.byref(rec), C.byref(n),
+                                       C.byref(used), C.byref(st))
+        if rc == -5:
+            return dict(status="erange", n=n.value)
+        self._ck(rc, "fl_reads_push_text")
+        out = {k: v[:n.value] for k, v in arr.items()}
+        out.update(status="fallback" if st.value else "ok", n=n.value, consumed=used.value)
+        return out
+
     def push_device(self, batch):
         self._ck(self.L.fl_reads_push_device(self.h, C.byref(batch)), "fl_reads_push_device")
 

@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 BUILD = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libfiltlong_b200.so")
-SOURCES = ["fl_api.cu", "fl_scan.cu", "fl_kmers.cu", "fl_score.cu", "fl_phred.cu", "fl_select.cu", "fl_comm.cu", "fl_synth.cu",
+SOURCES = ["fl_api.cu", "fl_scan.cu", "fl_kmers.cu", "fl_score.cu", "fl_phred.cu", "fl_select.cu", "fl_comm.cu", "fl_text.cu", "fl_synth.cu",
            "fl_synth_host.cpp"]
 HEADERS = ["fl_internal.cuh", "fl_device.cuh", "fl_synth.h", os.path.join("..", "..", "include", "filtlong_b200.h")]
 # host-only synthetic generators on their own (no CUDA inside): what bench.py's CPU legs load

@@ -67,6 +67,11 @@ class Batch(C.Structure):
     ]
 
 
+class TextRecords(C.Structure):
+    _fields_ = [("cap", C.c_uint64), ("name_off", C.c_void_p), ("name_len", C.c_void_p), ("comment_len", C.c_void_p),
+                ("seq_off", C.c_void_p), ("qual_off", C.c_void_p), ("len", C.c_void_p), ("name_hash", C.c_void_p)]
+
+
 class Summary(C.Structure):
     _fields_ = [
         ("min_q", C.c_double), ("max_q", C.c_double), ("mean_q", C.c_double), ("stdev_q", C.c_double),
@@ -126,6 +131,10 @@ SYMBOLS = [
     ("fl_kmers_bitmap_changed", C.c_int, [_P]),
     ("fl_kmers_release_build_state", C.c_int, [_P]),
     ("fl_reads_push", C.c_int, [_P, C.POINTER(Batch)]),
+    ("fl_reads_push_text", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.POINTER(TextRecords), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    ("fl_host_alloc", C.c_int, [C.c_uint64, C.POINTER(_P)]),
+    ("fl_host_free", None, [_P]),
     ("fl_reads_push_device", C.c_int, [_P, C.POINTER(Batch)]),
     ("fl_reads_reset", C.c_int, [_P]),
     ("fl_reads_count", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),

@@ -241,16 +241,6 @@ extern "C" void fl_phred_luts(int32_t window_size, double *q256, double *a256) {
 // thread per 32 bases (two 16-byte loads -> two sequence words + one mask word). Padding bytes produce
 // arbitrary codes; no kernel ever forms a 16-mer from bases at or beyond a sequence's length.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pack4(uint32_t x, uint32_t &code8, uint32_t &other4) {
-    x &= 0xDFDFDFDFu;                                     // fold lower case onto upper case
-    const uint32_t mA = __vcmpeq4(x, 0x41414141u), mC = __vcmpeq4(x, 0x43434343u), mG = __vcmpeq4(x, 0x47474747u),
-                   mT = __vcmpeq4(x, 0x54545454u);
-    const uint32_t v = ((mC | mT) & 0x01010101u) | ((mG | mT) & 0x02020202u);      // 2-bit code in every byte
-    code8 = (v * 0x40100401u) >> 24;                       // first character in bits 7:6 (no carries: fields never overlap)
-    const uint32_t o = ~(mA | mC | mG | mT) & 0x01010101u;
-    other4 = (o | (o >> 7) | (o >> 14) | (o >> 21)) & 0xFu; // first character in bit 0
-}
-
 __global__ void __launch_bounds__(256) k_pack_ascii(const uint8_t *__restrict__ ascii, unsigned long long groups,
                                                     uint32_t *__restrict__ seq2b, uint32_t *__restrict__ nmask) {
     const uint4 *in = reinterpret_cast<const uint4 *>(ascii);
@@ -262,7 +252,7 @@ __global__ void __launch_bounds__(256) k_pack_ascii(const uint8_t *__restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t code8, other4;
-            pack4(c[i], code8, other4);
+            fl_pack4(c[i], code8, other4);
             w[i >> 2] |= code8 << (24 - 8 * (i & 3));
             m |= other4 << (4 * i);
         }

@@ -132,3 +132,16 @@ __device__ __forceinline__ void fl_filter_slot(uint32_t kmer, unsigned log2_word
     word = h1 >> (32 - log2_words);
     bits = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
 }
+
+// Four characters -> four 2-bit codes (kmers.cpp:176-196: A/a 0, C/c 1, G/g 2, T/t 3, anything else 0), first
+// character in bits 7:6 of code8; other4 has bit i set where character i is not one of ACGTacgt.
+__device__ __forceinline__ void fl_pack4(uint32_t x, uint32_t &code8, uint32_t &other4) {
+    x &= 0xDFDFDFDFu;                                     // fold lower case onto upper case
+    const uint32_t mA = __vcmpeq4(x, 0x41414141u), mC = __vcmpeq4(x, 0x43434343u), mG = __vcmpeq4(x, 0x47474747u),
+                   mT = __vcmpeq4(x, 0x54545454u);
+    const uint32_t v = ((mC | mT) & 0x01010101u) | ((mG | mT) & 0x02020202u);      // 2-bit code in every byte
+    code8 = (v * 0x40100401u) >> 24;                       // first character in bits 7:6 (no carries: fields never overlap)
+    const uint32_t o = ~(mA | mC | mG | mT) & 0x01010101u;
+    other4 = (o | (o >> 7) | (o >> 14) | (o >> 21)) & 0xFu; // first character in bit 0
+}
+

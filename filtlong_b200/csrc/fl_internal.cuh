@@ -162,6 +162,7 @@ struct fl_ctx {
     DevVec<uint32_t> sc_pack_seq, sc_pack_nmask;   // 2-bit codes / non-ACGT mask packed on the device from an ASCII DEVICE batch
     DevVec<uint32_t> sc_mask;        // 1 bit per padded base: base covered by a reference 16-mer
     DevVec<uint32_t> sc_order;       // rows in descending-length bucket order
+    DevVec<uint32_t> tx_nl, tx_u32;  // fl_reads_push_text: newline positions; per-record name / comment / sequence / quality extents
     DevVec<int32_t> sc_items;        // length of each k_kmer_window item: the batch's reads, then its rows
     DevVec<unsigned long long> sc_u64a, sc_u64b, sc_u64c;
     DevVec<uint32_t> sc_u32a;

@@ -97,6 +97,7 @@ const Opt kOpts[] = {
     {0, "trim", false, "trim", "trim non-k-mer-matching bases from start/end of reads"},
     {0, "split", true, "split", "split reads at this many (or more) consecutive non-k-mer-matching bases (unit suffixes: k, kb, m, mb, g, gb)"},
     {0, "window_size", true, "int", "size of sliding window used when measuring window quality (default: 250)"},
+    {0, "gpus", true, "int", "number of B200 GPUs to shard the read set across (default: 1; not a reference option)"},
     {0, "verbose", false, "verbose", "verbose output to stderr with info for each read"},
     {0, "version", false, "version", "display the program version and quit"},
     {'h', "help", false, "help", "display this help menu"},
@@ -113,7 +114,7 @@ void print_help(const char *prog) {
         {"external references (if provided, read quality will be determined using these instead of from the Phred scores):", 6, 8},
         {"score weights (control the relative contribution of each score to the final read score):", 9, 11},
         {"read manipulation:", 12, 13},
-        {"other:", 14, 17},
+        {"other:", 14, 18},
     };
     for (const Group &g : groups) {
         o << g.title << "\n";
@@ -156,6 +157,7 @@ Arguments::Arguments(int argc, char **argv) {
         else if (ln == "trim") trim = true;
         else if (ln == "split") { split = read_int_suffix(nm, v); split_set = true; }
         else if (ln == "window_size") window_ll = read_plain_ll(nm, v);
+        else if (ln == "gpus") gpus = (int)read_plain_ll(nm, v);
         else if (ln == "verbose") verbose = true;
         else if (ln == "version") version_flag = true;
         else if (ln == "help") throw HelpRequested();
@@ -244,6 +246,7 @@ Arguments::Arguments(int argc, char **argv) {
     if (length_weight < 0.0 || mean_q_weight < 0.0 || window_q_weight < 0.0) FAIL("Error: weight values cannot be negative");
     if (split_set && split <= 0) FAIL("Error: the value for --split must be a positive integer");
     if (window_size <= 0) FAIL("Error: the value for --window_size must be a positive integer");
+    if (gpus < 1 || gpus > 64) FAIL("Error: the value for --gpus must be between 1 and 64");
 }
 
 bool Arguments::does_file_exist(const std::string &filename) {

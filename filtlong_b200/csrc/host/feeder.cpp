@@ -1,0 +1,474 @@
+// filtlong_b200/csrc/host/feeder.cpp -- see feeder.h.
+#include "feeder.h"
+
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/uio.h>
+#include <unistd.h>
+
+#include <stdlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "misc.h"
+#include "read.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// the input, mapped
+// ---------------------------------------------------------------------------------------------
+struct MappedFile {
+    const char *base = nullptr;
+    uint64_t size = 0;
+    int fd = -1;
+    bool open_plain(const std::string &path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 2) return false;
+        size = (uint64_t)st.st_size;
+        void *p = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) return false;
+        base = (const char *)p;
+        madvise(p, (size_t)size, MADV_SEQUENTIAL);
+        const unsigned char b0 = (unsigned char)base[0], b1 = (unsigned char)base[1];
+        return !(b0 == 0x1f && b1 == 0x8b);                    // gzip: the host reader inflates it
+    }
+    ~MappedFile() {
+        if (base) munmap((void *)base, (size_t)size);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+struct Chunk { uint64_t begin, end; };
+
+inline uint64_t eol(const char *b, uint64_t from, uint64_t size) {
+    if (from >= size) return size;
+    const void *p = memchr(b + from, '\n', (size_t)(size - from));
+    return p ? (uint64_t)((const char *)p - b) : size;
+}
+
+// Is `p` the first byte of a record? FASTQ: '@' line, a sequence line, a '+' line, a quality line as long as the
+// sequence (a quality line that begins with '@' fails the '+' test two lines on). FASTA: any line starting with '>'.
+bool record_starts_at(const char *b, uint64_t p, uint64_t size, int format) {
+    if (p >= size) return false;
+    if (format == FL_TEXT_FASTA) return b[p] == '>';
+    if (b[p] != '@') return false;
+    const uint64_t e0 = eol(b, p, size), s1 = e0 + 1, e1 = eol(b, s1, size), s2 = e1 + 1;
+    if (s2 >= size || b[s2] != '+') return false;
+    const uint64_t e2 = eol(b, s2, size), s3 = e2 + 1, e3 = eol(b, s3, size);
+    return s3 <= size && e3 - s3 == e1 - s1;
+}
+
+// record-aligned chunks of about `target` bytes; false if no boundary can be found (then the host parser runs)
+bool plan_chunks(const char *b, uint64_t size, int format, uint64_t target, uint64_t max_chunk, std::vector<Chunk> &out) {
+    uint64_t pos = 0;
+    while (pos < size) {
+        uint64_t end = size;
+        if (size - pos > target) {
+            uint64_t p = pos + target;                         // last record start at or before pos + target
+            bool found = false;
+            while (p > pos) {
+                const void *q = memrchr(b + pos, '\n', (size_t)(p - pos));
+                if (!q) break;
+                const uint64_t cand = (uint64_t)((const char *)q - b) + 1;
+                if (cand > pos && record_starts_at(b, cand, size, format)) { end = cand; found = true; break; }
+                p = cand - 1;
+                if (pos + target - p > (64ull << 20)) break;    // a single record this large: give up on the fast path
+            }
+            if (!found) return false;
+        }
+        if (end - pos > max_chunk) return false;
+        out.push_back(Chunk{pos, end});
+        pos = end;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one shard = one GPU = one context = one pusher thread + a ring of pinned chunks filled by copy threads
+// ---------------------------------------------------------------------------------------------
+struct Records {                      // per shard, in file order; offsets are FILE offsets
+    std::vector<uint64_t> name_off, seq_off, qual_off, name_hash;
+    std::vector<uint32_t> name_len, comment_len;
+    std::vector<int32_t> len;
+    size_t n = 0;
+    void ensure(size_t cap) {
+        if (name_off.size() >= cap) return;
+        const size_t c = cap + cap / 2;
+        name_off.resize(c); seq_off.resize(c); qual_off.resize(c); name_hash.resize(c);
+        name_len.resize(c); comment_len.resize(c); len.resize(c);
+    }
+};
+
+struct Shard {
+    int index = 0, device = 0;
+    fl_ctx *ctx = nullptr;
+    bool owns_ctx = false;
+    size_t chunk_lo = 0, chunk_hi = 0;          // chunks [lo, hi) of the plan
+    Records rec;
+    // results needed by the writer
+    std::vector<int32_t> n_child, row_s, row_e;
+    std::vector<uint64_t> row_start;
+    std::vector<uint8_t> row_pfinal;
+    uint64_t n_rows = 0;
+    fl_summary summary{};
+    std::string error;
+    bool fallback = false;
+};
+
+struct Ring {
+    static constexpr int K = 3;
+    char *slot[K] = {nullptr, nullptr, nullptr};
+    int state[K] = {0, 0, 0};                   // 0 free, 1 filled
+    std::mutex m;
+    std::condition_variable cv;
+};
+
+void check(fl_ctx *c, int rc, const char *what) {
+    if (rc != FL_OK) throw std::runtime_error(std::string(what) + ": " + fl_last_error(c));
+}
+
+void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, int format, const fl_params &params, int nranks,
+               const unsigned char *comm_id, fl_ctx *ctx0, std::atomic<bool> &abort_all, uint64_t max_chunk, bool share_kmers) {
+    Ring ring;
+    std::vector<std::thread> copiers;
+    try {
+        if (sh.index == 0) sh.ctx = ctx0;
+        else {
+            if (fl_ctx_create(&params, sh.device, &sh.ctx) != FL_OK) throw std::runtime_error(std::string("fl_ctx_create: ") + fl_last_error(nullptr));
+            sh.owns_ctx = true;
+        }
+        check(sh.ctx, fl_ctx_set_params(sh.ctx, &params), "fl_ctx_set_params");
+        if (nranks > 1) {
+            check(sh.ctx, fl_comm_init(sh.ctx, comm_id, sh.index, nranks), "fl_comm_init");
+            if (share_kmers) {
+                check(sh.ctx, fl_kmers_broadcast(sh.ctx, 0), "fl_kmers_broadcast");   // Kmers built once (main.cpp:53-59), used by every shard
+                uint64_t nk = 0;
+                check(sh.ctx, fl_kmers_finalize(sh.ctx, &nk), "fl_kmers_finalize");
+            }
+        }
+        for (int k = 0; k < Ring::K; ++k) {
+            void *p = nullptr;
+            if (fl_host_alloc(max_chunk + 64, &p) != FL_OK) throw std::runtime_error("pinned chunk ring: out of memory");
+            ring.slot[k] = (char *)p;
+        }
+        // copy threads: chunk i of the shard goes through slot i % K
+        const size_t n_chunks = sh.chunk_hi - sh.chunk_lo;
+        for (int k = 0; k < Ring::K; ++k)
+            copiers.emplace_back([&, k] {
+                for (size_t i = (size_t)k; i < n_chunks; i += Ring::K) {
+                    {
+                        std::unique_lock<std::mutex> lk(ring.m);
+                        ring.cv.wait(lk, [&] { return ring.state[k] == 0 || abort_all.load(); });
+                        if (abort_all.load()) return;
+                    }
+                    const Chunk &c = plan[sh.chunk_lo + i];
+                    memcpy(ring.slot[k], f.base + c.begin, (size_t)(c.end - c.begin));
+                    {
+                        std::lock_guard<std::mutex> lk(ring.m);
+                        ring.state[k] = 1;
+                    }
+                    ring.cv.notify_all();
+                }
+            });
+        size_t guess = 1024;
+        for (size_t i = 0; i < n_chunks && !abort_all.load(); ++i) {
+            const int k = (int)(i % Ring::K);
+            {
+                std::unique_lock<std::mutex> lk(ring.m);
+                ring.cv.wait(lk, [&] { return ring.state[k] == 1 || abort_all.load(); });
+                if (abort_all.load()) break;
+            }
+            const Chunk &c = plan[sh.chunk_lo + i];
+            const uint64_t nb = c.end - c.begin;
+            const bool last = sh.chunk_lo + i + 1 == plan.size();
+            if (i == 0) guess = (size_t)(nb / 256) + 1024;
+            for (;;) {
+                Records &R = sh.rec;
+                R.ensure(R.n + guess);
+                fl_text_records out{};
+                out.cap = guess;
+                out.name_off = R.name_off.data() + R.n; out.name_len = R.name_len.data() + R.n; out.comment_len = R.comment_len.data() + R.n;
+                out.seq_off = R.seq_off.data() + R.n; out.qual_off = R.qual_off.data() + R.n; out.len = R.len.data() + R.n;
+                out.name_hash = R.name_hash.data() + R.n;
+                uint64_t n_rec = 0, used = 0;
+                int status = 0;
+                const int rc = fl_reads_push_text(sh.ctx, ring.slot[k], nb, format, last ? 1 : 0, &out, &n_rec, &used, &status);
+                if (rc == FL_ERANGE && n_rec > guess) { guess = (size_t)n_rec + 16; continue; }
+                check(sh.ctx, rc, "fl_reads_push_text");
+                if (status != FL_TEXT_OK || used != nb) { sh.fallback = true; abort_all.store(true); break; }
+                for (size_t j = R.n; j < R.n + n_rec; ++j) {            // chunk offsets -> file offsets
+                    R.name_off[j] += c.begin; R.seq_off[j] += c.begin; R.qual_off[j] += c.begin;
+                }
+                R.n += (size_t)n_rec;
+                guess = (size_t)n_rec + (size_t)n_rec / 4 + 1024;
+                break;
+            }
+            {
+                std::lock_guard<std::mutex> lk(ring.m);
+                ring.state[k] = 0;
+            }
+            ring.cv.notify_all();
+        }
+    } catch (const std::exception &e) {
+        sh.error = e.what();
+        abort_all.store(true);
+    }
+    ring.cv.notify_all();
+    for (auto &t : copiers) t.join();
+    for (int k = 0; k < Ring::K; ++k) fl_host_free(ring.slot[k]);
+}
+
+// main.cpp:169-261 on every shard (collective over NCCL when there are several), then the arrays the writer needs
+void finalize_shard(Shard &sh) {
+    try {
+        check(sh.ctx, fl_finalize(sh.ctx, -1, &sh.summary), "fl_finalize");
+        uint64_t nr = 0, nw = 0;
+        check(sh.ctx, fl_reads_count(sh.ctx, &nr, &nw, nullptr), "fl_reads_count");
+        sh.n_rows = nw;
+        sh.n_child.resize(nr); sh.row_start.resize(nr);
+        sh.row_s.resize(nw); sh.row_e.resize(nw); sh.row_pfinal.resize(nw);
+        fl_read_results rr{};
+        rr.n_child = sh.n_child.data(); rr.row_start = sh.row_start.data();
+        check(sh.ctx, fl_results_reads(sh.ctx, &rr), "fl_results_reads");
+        fl_row_results wr{};
+        wr.start = sh.row_s.data(); wr.end = sh.row_e.data(); wr.passed_final = sh.row_pfinal.data();
+        check(sh.ctx, fl_results_rows(sh.ctx, &wr), "fl_results_rows");
+    } catch (const std::exception &e) {
+        sh.error = e.what();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// duplicate names (main.cpp:113-117) at scale: a flat open-addressing table over the 64-bit hashes the
+// device computed, names compared byte for byte in the mapping only when two hashes agree
+// ---------------------------------------------------------------------------------------------
+struct NameRef { uint64_t off; uint32_t len; };
+
+bool find_duplicate(const std::vector<Shard> &shards, const char *base, std::string *dup) {
+    size_t n = 0;
+    for (auto &s : shards) n += s.rec.n;
+    size_t cap = 16;
+    while (cap < 2 * n + 16) cap <<= 1;
+    std::vector<uint64_t> keys(cap, 0);
+    std::vector<NameRef> vals(cap);
+    std::vector<uint8_t> used(cap, 0);
+    for (auto &s : shards)
+        for (size_t i = 0; i < s.rec.n; ++i) {
+            const uint64_t h = s.rec.name_hash[i];
+            size_t slot = (size_t)(h * 0x9E3779B97F4A7C15ull) & (cap - 1);
+            for (;;) {
+                if (!used[slot]) {
+                    used[slot] = 1; keys[slot] = h; vals[slot] = NameRef{s.rec.name_off[i], s.rec.name_len[i]};
+                    break;
+                }
+                if (keys[slot] == h && vals[slot].len == s.rec.name_len[i] &&
+                    memcmp(base + vals[slot].off, base + s.rec.name_off[i], s.rec.name_len[i]) == 0) {
+                    dup->assign(base + s.rec.name_off[i], s.rec.name_len[i]);
+                    return true;
+                }
+                slot = (slot + 1) & (cap - 1);
+            }
+        }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: the survivors, in input order, straight out of the mapping (main.cpp:263-313)
+// ---------------------------------------------------------------------------------------------
+struct Writer {
+    static constexpr int MAXV = 1000;
+    struct iovec v[MAXV];
+    int nv = 0;
+    std::vector<std::string> small;            // child names: must stay alive until the flush
+    bool failed = false;
+    void flush() {
+        int done = 0;
+        while (done < nv && !failed) {
+            ssize_t w = writev(STDOUT_FILENO, v + done, nv - done);
+            if (w < 0) { failed = true; break; }
+            while (done < nv && (size_t)w >= v[done].iov_len) { w -= (ssize_t)v[done].iov_len; ++done; }
+            if (done < nv && w > 0) { v[done].iov_base = (char *)v[done].iov_base + w; v[done].iov_len -= (size_t)w; }
+        }
+        nv = 0;
+        small.clear();
+    }
+    void put(const void *p, size_t n) {
+        if (n == 0) return;
+        if (nv == MAXV) flush();
+        v[nv].iov_base = const_cast<void *>(p);
+        v[nv].iov_len = n;
+        ++nv;
+    }
+    void put_owned(std::string s) {
+        if (nv == MAXV || small.size() >= 200) flush();
+        small.push_back(std::move(s));
+        put(small.back().data(), small.back().size());
+    }
+};
+
+}  // namespace
+
+FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function<void(const char *)> &mark) {
+    FeederOutcome res;
+    if (args.verbose || getenv("FL_HOST_PARSER")) return res;           // per-read dumps come from the host path
+    MappedFile f;
+    if (!f.open_plain(args.input_reads)) return res;
+    const int format = f.base[0] == '@' ? FL_TEXT_FASTQ : (f.base[0] == '>' ? FL_TEXT_FASTA : 0);
+    if (!format) return res;
+    const bool kmers_empty = kmers.empty();
+    if (format == FL_TEXT_FASTA && kmers_empty) return res;             // main.cpp:103-106: the host path prints the error
+    uint64_t target = 256ull << 20;
+    if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
+    if (target < (1ull << 20)) target = 1ull << 20;
+    const uint64_t max_chunk = target + (64ull << 20) > (2047ull << 20) ? (2047ull << 20) : target + (64ull << 20);
+    int nranks = args.gpus;
+    std::vector<Chunk> plan;
+    if (!plan_chunks(f.base, f.size, format, target, max_chunk, plan) || plan.empty()) return res;
+    if ((size_t)nranks > plan.size()) nranks = (int)plan.size();         // tiny inputs: fewer shards than GPUs asked for
+
+    fl_ctx *ctx0 = kmers.context();
+    const fl_params params = params_from_arguments(args);
+    unsigned char comm_id[FL_COMM_ID_BYTES] = {0};
+    if (nranks > 1 && fl_comm_unique_id(comm_id) != FL_OK) throw std::runtime_error("NCCL is not available: cannot shard across GPUs");
+    // contiguous chunk ranges, balanced by bytes (file order is kept: shard r holds the records before shard r + 1's)
+    std::vector<Shard> shards((size_t)nranks);
+    {
+        size_t c = 0;
+        for (int r = 0; r < nranks; ++r) {
+            shards[r].index = r;
+            shards[r].device = r;
+            shards[r].chunk_lo = c;
+            const uint64_t goal = f.size / (uint64_t)nranks * (uint64_t)(r + 1);
+            while (c < plan.size() && (r + 1 == nranks || plan[c].end <= goal || c == shards[r].chunk_lo)) ++c;
+            shards[r].chunk_hi = c;
+        }
+        shards.back().chunk_hi = plan.size();
+    }
+    std::atomic<bool> abort_all(false);
+    {
+        std::vector<std::thread> ts;
+        for (int r = 1; r < nranks; ++r)
+            ts.emplace_back(run_shard, std::ref(shards[r]), std::cref(f), std::cref(plan), format, std::cref(params), nranks, comm_id, ctx0,
+                            std::ref(abort_all), max_chunk, !kmers_empty);
+        run_shard(shards[0], f, plan, format, params, nranks, comm_id, ctx0, abort_all, max_chunk, !kmers_empty);
+        for (auto &t : ts) t.join();
+    }
+    auto cleanup = [&]() {
+        for (auto &s : shards) {
+            if (s.ctx && nranks > 1) fl_comm_destroy(s.ctx);
+            if (s.owns_ctx && s.ctx) fl_ctx_destroy(s.ctx);
+        }
+    };
+    for (auto &s : shards)
+        if (!s.error.empty()) { cleanup(); throw std::runtime_error(s.error); }
+    if (abort_all.load()) {                                             // not the simple layout after all: start over on the host
+        fl_reads_reset(ctx0);
+        cleanup();
+        return res;
+    }
+    mark("pass 1 (device parse + score)");
+    res.handled = true;
+    std::cerr << "Scoring long reads\n";
+    long long n_reads = 0, total_bases = 0;
+    for (auto &s : shards) {
+        n_reads += (long long)s.rec.n;
+        for (size_t i = 0; i < s.rec.n; ++i) total_bases += s.rec.len[i];
+    }
+    print_read_score_progress(n_reads, total_bases);
+    std::cerr << "\n";
+    {
+        std::string dup;
+        if (find_duplicate(shards, f.base, &dup)) {
+            std::cerr << "Error: duplicate read name: " << dup << "\n";
+            cleanup();
+            res.exit_code = 1;
+            return res;
+        }
+    }
+    mark("duplicate-name check");
+    // ---- normalise, final score, target (main.cpp:136-261) ----
+    {
+        std::vector<std::thread> ts;
+        for (int r = 1; r < nranks; ++r) ts.emplace_back(finalize_shard, std::ref(shards[r]));
+        finalize_shard(shards[0]);
+        for (auto &t : ts) t.join();
+    }
+    for (auto &s : shards)
+        if (!s.error.empty()) { cleanup(); throw std::runtime_error(s.error); }
+    mark("finalize + download");
+    const fl_summary &summary = shards[0].summary;
+    uint64_t n_rows = 0;
+    for (auto &s : shards) n_rows += s.n_rows;
+    if (args.trim || args.split_set) {
+        if (args.trim && args.split_set) std::cerr << "  after trimming and splitting: ";
+        else if (args.trim) std::cerr << "  after trimming: ";
+        else std::cerr << "  after splitting: ";
+        std::cerr << int_to_string((long long)n_rows) << " reads (" << int_to_string(summary.rows_bases) << " bp)\n";
+    }
+    std::cerr << "\n";
+    if (args.target_bases_set || args.keep_percent_set) {
+        std::cerr << "Filtering long reads\n";
+        std::cerr << "  target: " << int_to_string(summary.target) << " bp\n";
+        if (summary.status == 1) std::cerr << "  not enough reads to reach target\n";
+        else if (summary.status == 2) std::cerr << "  reads already fall below target after filtering\n";
+        else std::cerr << "  keeping " << int_to_string(summary.keeping) << " bp\n";
+        std::cerr << "\n";
+    }
+    // ---- pass 2 ----
+    std::cerr << "Outputting passed long reads\n";
+    fflush(stdout);
+    Writer w;
+    const char lead = format == FL_TEXT_FASTA ? '>' : '@';
+    static const char plus_nl[] = "+\n", nl[] = "\n", sp[] = " ";
+    for (auto &s : shards) {
+        const Records &R = s.rec;
+        for (size_t i = 0; i < R.n; ++i) {
+            const size_t rs = (size_t)s.row_start[i];
+            const int nc = s.n_child[i];
+            if (nc == 0) {
+                if (!s.row_pfinal[rs]) continue;
+                // header line, sequence, '+', quality are contiguous in the file except for the '+' line's text: two slices
+                w.put(f.base + R.name_off[i] - 1, 1 + (size_t)R.name_len[i]);                        // '@' / '>' + name
+                if (R.comment_len[i]) { w.put(sp, 1); w.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
+                w.put(nl, 1);
+                w.put(f.base + R.seq_off[i], (size_t)R.len[i]);
+                w.put(nl, 1);
+                if (format == FL_TEXT_FASTQ) { w.put(plus_nl, 2); w.put(f.base + R.qual_off[i], (size_t)R.len[i]); w.put(nl, 1); }
+            } else {
+                for (int c = 0; c < nc; ++c) {
+                    const size_t row = rs + (size_t)c;
+                    if (!s.row_pfinal[row]) continue;
+                    const int start = s.row_s[row], length = s.row_e[row] - s.row_s[row];
+                    if (length <= 0) continue;
+                    std::string nm(1, lead);
+                    nm.append(f.base + R.name_off[i], R.name_len[i]);
+                    nm += "_" + std::to_string(start + 1) + "-" + std::to_string(s.row_e[row]);      // read.cpp:135-136
+                    w.put_owned(std::move(nm));
+                    if (R.comment_len[i]) { w.put(sp, 1); w.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
+                    w.put(nl, 1);
+                    w.put(f.base + R.seq_off[i] + start, (size_t)length);
+                    w.put(nl, 1);
+                    if (format == FL_TEXT_FASTQ) { w.put(plus_nl, 2); w.put(f.base + R.qual_off[i] + start, (size_t)length); w.put(nl, 1); }
+                }
+            }
+        }
+    }
+    w.flush();
+    mark("pass 2 (slices of the mapped input)");
+    std::cerr << "\n";
+    cleanup();
+    res.exit_code = w.failed ? 1 : 0;
+    return res;
+}

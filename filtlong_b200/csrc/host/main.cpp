@@ -24,6 +24,7 @@
 
 #include "arguments.h"
 #include "fastx.h"
+#include "feeder.h"
 #include "kmers.h"
 #include "misc.h"
 #include "read.h"
@@ -78,6 +79,12 @@ int main(int argc, char **argv) {
         if (!args.short_reads.empty()) kmers.add_read_fastqs(args.short_reads);
         const bool kmers_empty = kmers.empty();
         timer.mark("reference k-mers (+ CUDA init)");
+
+        // ---- the B200-first input path: the file as text to the device, survivors by writev from the mapping ----
+        {
+            const FeederOutcome fo = run_text_feeder(args, kmers, [&](const char *what) { timer.mark(what); });
+            if (fo.handled) return fo.exit_code;
+        }
 
         // ---- pass 1: parse, pack and score (main.cpp:61-130) ----
         long long total_bases = 0, last_progress = 0;

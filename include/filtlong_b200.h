@@ -154,6 +154,34 @@ int fl_kmers_release_build_state(fl_ctx *ctx);
 int fl_reads_push(fl_ctx *ctx, const fl_batch *host_batch);
 /* Same with the arena already resident in device memory (no copies). */
 int fl_reads_push_device(fl_ctx *ctx, const fl_batch *dev_batch);
+/* The feeder (replaces the kseq_read loop of main.cpp:70-125 for the common file layout): hands a chunk of
+ * the input FILE -- bytes, as mapped -- to the device, which finds the record boundaries, validates them,
+ * extracts per-record extents and a 64-bit hash of every name (for the duplicate check of main.cpp:113-117),
+ * packs the sequences (k-mer mode) or gathers the qualities (Phred mode) into the arena and scores the
+ * records like fl_reads_push. The chunk must START at a record boundary; records are 4-line FASTQ
+ * (FL_TEXT_FASTQ) or 2-line FASTA (FL_TEXT_FASTA) with LF line ends. *bytes_consumed = end of the last whole
+ * record (the caller starts its next chunk there); with is_last_chunk the final line may lack its newline.
+ * FL_ERANGE: out->cap is too small; nothing was scored and *n_records holds the number needed.
+ * If the text is not in that layout (CR LF, multi-line records, blank lines, quality / sequence length
+ * mismatch ...) nothing is scored and *status = FL_TEXT_FALLBACK: the caller parses on the host instead
+ * (kseq semantics, and the reference's error messages for broken input). Offsets in `out` are relative to the
+ * chunk's first byte; comment_len == 0 means no comment, otherwise it starts at name_off + name_len + 1. */
+enum { FL_TEXT_FASTQ = 1, FL_TEXT_FASTA = 2 };
+enum { FL_TEXT_OK = 0, FL_TEXT_FALLBACK = 1 };
+typedef struct fl_text_records {
+    uint64_t cap;                      /* capacity of each array, in records */
+    uint64_t *name_off;                /* any array may be NULL */
+    uint32_t *name_len, *comment_len;
+    uint64_t *seq_off, *qual_off;
+    int32_t *len;
+    uint64_t *name_hash;
+} fl_text_records;
+int fl_reads_push_text(fl_ctx *ctx, const char *host_text, uint64_t n_bytes, int format, int is_last_chunk,
+                       const fl_text_records *out, uint64_t *n_records, uint64_t *bytes_consumed, int *status);
+/* Page-locked host memory for the caller's chunk ring (portable across devices); the host side of the
+ * boundary links no CUDA runtime of its own. */
+int fl_host_alloc(uint64_t n_bytes, void **out);
+void fl_host_free(void *p);
 /* Forget all scored reads (keeps the k-mer set and parameters). */
 int fl_reads_reset(fl_ctx *ctx);
 /* Number of input reads / of "reads2" rows (children replace their parent, main.cpp:138-147). */

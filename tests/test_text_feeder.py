@@ -1,0 +1,200 @@
+"""The feeder: FASTQ / FASTA text parsed on the device (fl_reads_push_text) and the CLI's
+input path built on it (mapped file -> pinned ring -> device; writev output from the mapping; duplicate
+names through device-computed hashes). Results must equal the packed-arena path bit for bit, the record index
+must equal a plain Python parse, anything outside the simple layout must be handed back (FALLBACK) untouched,
+and the CLI's stdout must stay byte-identical to the reference binary's."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from filtlong_b200 import api
+from oracle import oracle as orc
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "filtlong_b200", "bin", "filtlong")
+
+
+def fastq_text(reads, last_newline=True):
+    t = b"".join(b"@" + n + b"\n" + s + b"\n+" + (n if i % 3 == 0 else b"") + b"\n" + q + b"\n" for i, (n, s, q) in enumerate(reads))
+    return t if last_newline else t[:-1]
+
+
+def make_reads(seed, n=120, genome=None):
+    rng = np.random.default_rng(seed)
+    genome = genome or util.rand_seq(rng, 50000)
+    reads = [(("read_%d" % i).encode() + (b" comment %d\twith tab" % i if i % 4 == 1 else b""), s, q)
+             for i, (_, s, q) in enumerate(util.long_reads(rng, genome, n, max_len=7000))]
+    reads.append((b"x", b"ACGT", b"IIII"))
+    reads.append((b"a_rather_long_name_" * 5, util.rand_seq(rng, 33), b"5" * 33))
+    return genome, reads
+
+
+@pytest.mark.parametrize("mode", ["phred", "kmer"])
+@pytest.mark.parametrize("last_newline", [True, False])
+def test_push_text_equals_packed_path_and_python_parse(mode, last_newline):
+    genome, reads = make_reads(3)
+    opts = dict(keep_percent=70.0) if mode == "phred" else dict(keep_percent=70.0, trim=True, split=120)
+    text = fastq_text(reads, last_newline)
+    ctx = api.Context(api.make_params(**opts))
+    ref = api.Context(api.make_params(**opts))
+    if mode == "kmer":
+        for c in (ctx, ref):
+            c.kmers_add([genome], False)
+            c.kmers_count()
+    # the text in three record-aligned chunks (the caller's job: fl_reads_push_text reports where whole records end)
+    cuts, pos = [], 0
+    idx = {k: [] for k in ("name_off", "name_len", "comment_len", "seq_off", "qual_off", "len", "name_hash")}
+    while pos < len(text):
+        piece = text[pos:pos + len(text) // 3 + 1000]
+        is_last = pos + len(piece) >= len(text)
+        if not is_last:                        # cut at a record boundary: last "\n@" followed by a well formed record
+            k = piece.rfind(b"\n@")
+            while True:
+                rest = piece[k + 1:].split(b"\n")
+                if len(rest) >= 4 and rest[2].startswith(b"+") and len(rest[1]) == len(rest[3]):
+                    break
+                k = piece.rfind(b"\n@", 0, k)
+            piece = piece[:k + 1]
+        r = ctx.push_text(piece, fastq=True, is_last=is_last)
+        assert r["status"] == "ok" and r["consumed"] == len(piece)
+        for k in idx:
+            idx[k].append(r[k] + (pos if k.endswith("_off") else 0) if k.endswith("_off") else r[k])
+        cuts.append(r["n"])
+        pos += len(piece)
+    idx = {k: np.concatenate(v) for k, v in idx.items()}
+    assert sum(cuts) == len(reads) and len(cuts) >= 3
+    for i, (n, s, q) in enumerate(reads):
+        name, _, comment = n.partition(b" ")
+        o = int(idx["name_off"][i])
+        assert text[o:o + int(idx["name_len"][i])] == name
+        assert int(idx["comment_len"][i]) == len(comment)
+        if comment:
+            assert text[o + len(name) + 1:o + len(name) + 1 + len(comment)] == comment
+        assert int(idx["len"][i]) == len(s)
+        assert text[int(idx["seq_off"][i]):int(idx["seq_off"][i]) + len(s)] == s
+        assert text[int(idx["qual_off"][i]):int(idx["qual_off"][i]) + len(q)] == q
+    # equal names <=> equal hashes (here: all distinct)
+    assert len(set(idx["name_hash"].tolist())) == len(reads)
+    ref.push(api.HostBatch([r[1] for r in reads], [r[2] for r in reads], want_seq=(mode == "kmer")))
+    s1, s2 = ctx.finalize(-1), ref.finalize(-1)
+    assert (s1.status, s1.target, s1.keeping, s1.total_bases) == (s2.status, s2.target, s2.keeping, s2.total_bases)
+    a, b = ctx.row_results(), ref.row_results()
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+    ra, rb = ctx.read_results(), ref.read_results()
+    for k in ra:
+        assert np.array_equal(ra[k].view(np.uint8), rb[k].view(np.uint8)), k
+    ctx.close(); ref.close()
+
+
+def test_push_text_fasta_and_fallbacks():
+    genome, reads = make_reads(5, n=30)
+    ctx = api.Context(api.make_params(keep_percent=80.0))
+    fasta = b"".join(b">" + n + b"\n" + s + b"\n" for n, s, _ in reads)
+    assert ctx.push_text(fasta, fastq=False)["status"] == "fallback"          # no reference: main.cpp:103-106 is the host's error
+    ctx.kmers_add([genome], False)
+    ctx.kmers_count()
+    r = ctx.push_text(fasta, fastq=False)
+    assert r["status"] == "ok" and r["n"] == len(reads) and [int(x) for x in r["len"]] == [len(s) for _, s, _ in reads]
+    ctx.reset_reads()
+    good = fastq_text(reads)
+    crlf = good.replace(b"\n", b"\r\n")
+    two_line_seq = b"@a\nACGT\nACGT\n+\nIIIIIIII\n"
+    short_qual = b"@a\nACGTACGT\n+\nIIII\n@b\nACGT\n+\nIIII\n"
+    blank = b"@a\nACGT\n+\nIIII\n\n@b\nACGT\n+\nIIII\n"
+    no_name = b"@\nACGT\n+\nIIII\n"
+    empty_seq = b"@a\n\n+\n\n"
+    wrong_lead = b">a\nACGT\n+\nIIII\n"
+    for bad in (crlf, two_line_seq, short_qual, blank, no_name, empty_seq, wrong_lead):
+        r = ctx.push_text(bad, fastq=True)
+        assert r["status"] == "fallback", bad[:40]
+        assert ctx.counts()[0] == 0                      # nothing was scored
+    # too small a record array: the needed size comes back, nothing scored
+    r = ctx.push_text(good, fastq=True, cap=5)
+    assert r["status"] == "erange" and r["n"] == len(reads) and ctx.counts()[0] == 0
+    # a truncated final record in a chunk that is not the last: whole records are consumed, the rest is the caller's
+    r = ctx.push_text(good + b"@tail\nACG", fastq=True, is_last=False)
+    assert r["status"] == "ok" and r["n"] == len(reads) and r["consumed"] == len(good)
+    ctx.close()
+
+
+def run(cmd, env=None):
+    e = dict(os.environ, LC_ALL="C")
+    e.pop("LANG", None)
+    e.update(env or {})
+    p = subprocess.run(cmd, capture_output=True, env=e)
+    return p.returncode, p.stdout, p.stderr.decode(errors="replace")
+
+
+CLI_CASES = [
+    ["--min_length", "1", "--keep_percent", "90", "FQ"],
+    ["-t", "300000", "FQ"],
+    ["-p", "60", "--min_mean_q", "70", "--window_size", "100", "FQ"],
+    ["-t", "1g", "FQ"],
+    ["-a", "FA", "-p", "90", "FQ"],
+    ["-a", "FA", "-p", "80", "--trim", "--split", "100", "FQ"],
+    ["-a", "FA", "--split", "30", "-t", "250000", "FQ"],
+    ["-a", "FA", "-p", "70", "--trim", "--split", "80", "FASTA"],
+]
+
+
+@pytest.mark.parametrize("case", CLI_CASES, ids=lambda c: " ".join(c))
+@pytest.mark.parametrize("last_newline", [True, False])
+def test_cli_device_parse_path_is_byte_identical_to_the_reference(case, last_newline, tmp_path):
+    if not (os.path.exists(CLI) and orc.have_ref()):
+        pytest.skip("CLI or reference binary not built")
+    genome, reads = make_reads(11, n=200)
+    fq = tmp_path / "reads.fastq"
+    fq.write_bytes(fastq_text(reads, last_newline))
+    fa = util.write_fasta(tmp_path / "asm.fasta", [("contig_1", genome[:30000]), ("contig_2", genome[30000:])], width=60)
+    fasta = tmp_path / "reads.fasta"
+    fasta.write_bytes(b"".join(b">" + n + b"\n" + s + b"\n" for n, s, _ in reads[:80]))
+    sub = {"FQ": str(fq), "FA": fa, "FASTA": str(fasta)}
+    args = [sub.get(a, a) for a in case]
+    rc_r, out_r, err_r = run([orc.REFCLI] + args)
+    # tiny chunks so that the plan has many of them and the ring wraps
+    rc_o, out_o, err_o = run([CLI] + args, {"FL_CLI_TIMING": "1", "FL_CHUNK_MB": "1"})
+    assert rc_o == rc_r == 0, err_o[-2000:]
+    assert "device parse" in err_o, "the host parser ran instead of the feeder"
+    assert out_o == out_r
+    rc_h, out_h, err_h = run([CLI] + args, {"FL_HOST_PARSER": "1"})
+    assert rc_h == 0 and out_h == out_r
+    tail = lambda e: [l.split("\r")[-1] for l in e.splitlines() if l.strip() and "[timing]" not in l and "bp)" not in l]
+    assert tail(err_o) == tail(err_r)
+
+
+def test_cli_duplicate_names_and_fallback_inputs(tmp_path):
+    if not (os.path.exists(CLI) and orc.have_ref()):
+        pytest.skip("CLI or reference binary not built")
+    rng = np.random.default_rng(2)
+    recs = [(b"r%d" % i, util.rand_seq(rng, 300), util.rand_qual(rng, 300)) for i in range(400)]
+    dup = tmp_path / "dup.fastq"
+    dup.write_bytes(fastq_text(recs + [(b"r37", util.rand_seq(rng, 100), b"I" * 100)] + recs[:3]))
+    multi = tmp_path / "multi.fastq"                       # a two-line sequence in the middle: the feeder must hand the file back
+    multi.write_bytes(fastq_text(recs[:100]) + b"@ml\nACGTACGT\nACGT\n+\nIIIIIIIIIIII\n" + fastq_text(recs[100:200]))
+    for path in (dup, multi):
+        args = ["-p", "50", str(path)]
+        rc_r, out_r, err_r = run([orc.REFCLI] + args)
+        rc_o, out_o, err_o = run([CLI] + args, {"FL_CHUNK_MB": "1"})
+        assert (rc_o, out_o) == (rc_r, out_r)
+        assert [l for l in err_o.splitlines() if l.startswith("Error")] == [l for l in err_r.splitlines() if l.startswith("Error")]
+
+
+def test_cli_sharded_over_gpus_prints_what_one_gpu_prints(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    genome, reads = make_reads(21, n=600)
+    reads = reads + [(n + b"_again", s, q) for n, s, q in reads[:50]]          # exact score ties across shards
+    fq = tmp_path / "reads.fastq"
+    fq.write_bytes(fastq_text(reads))
+    fa = util.write_fasta(tmp_path / "asm.fasta", [("c", genome)])
+    for case in (["-p", "60", str(fq)], ["-a", fa, "-p", "70", "--trim", "--split", "100", str(fq)]):
+        rc1, out1, err1 = run([CLI] + case, {"FL_CHUNK_MB": "1"})
+        rc2, out2, err2 = run([CLI, "--gpus", "2"] + case, {"FL_CHUNK_MB": "1"})
+        assert rc1 == rc2 == 0, err2[-2000:]
+        assert out1 == out2
