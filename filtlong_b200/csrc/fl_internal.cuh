@@ -117,7 +117,7 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    int filter_kind = 3;                 // bit 0: word from the k-mer's minimizer (loads de-duplicated per lane) instead of a plain hash; bit 1: ld.global.cg (FL_FILTER_KIND)
+    int filter_kind = 2;                 // bit 0: word from the k-mer's minimizer (loads de-duplicated per lane) instead of a plain hash; bit 1: ld.global.cg (FL_FILTER_KIND)
     bool use_filter = false;
     uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
     bool use_anchor = false;
@@ -139,7 +139,7 @@ struct fl_ctx {
     unsigned long long tie_many = 0;        // bit e: more than one table value ties there
     unsigned char tie_char[64] = {0};       // the one that does, when exactly one
     unsigned long long tie_binades_a = 0;   // bit e: some window-table value ties when w is in [2^-e, 2^(1-e))
-    int phred_mode = 1;                     // 1: k_phred_score, sum + window fused (default); 2: k_phred_sum + k_phred_win; 0: work-item kernels (FL_PHRED_MODE)
+    int phred_mode = 2;                     // 2: k_phred_sum + k_phred_win (default: measured faster); 1: k_phred_score, both fused in one pass; 0: work-item kernels (FL_PHRED_MODE)
     int phred_occupancy = 0;                // blocks per SM launched for the Phred kernels, 0 = the kernel's own default (FL_PHRED_OCC)
     int lut_window = -1;
     bool phred_attr_set = false, phred_items_attr_set = false;   // cudaFuncSetAttribute is per DEVICE: kept per context

@@ -1153,7 +1153,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
     const int ws = ctx->p.window_size;
     if ((ctx->phred_mode == 1 || ctx->phred_mode == 2) && ws >= 16 && ws <= 256) {
-        const bool fused = ctx->phred_mode == 1;            // default: k_phred_score; 2: k_phred_sum + k_phred_win (comparison)
+        const bool fused = ctx->phred_mode == 1;            // 1: k_phred_score (one pass); 2: k_phred_sum + k_phred_win
         // default: one warp per read, both chains by exact grid arithmetic (k_phred_sum, k_phred_win)
         FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
         FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));

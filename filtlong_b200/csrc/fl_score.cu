@@ -639,15 +639,8 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                 }
                 hits += __popc(in);
                 const uint32_t pin = in & ~out, pout = out & ~in, both = in & out;
-                int delta = 0, mn = 99, mx = -99;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const unsigned e = lut[((pin >> (4 * q)) & 15u) | (((pout >> (4 * q)) & 15u) << 4)];
-                    const int lo_q = delta + (int)((e >> 4) & 15u) - 4, hi_q = delta + (int)((e >> 8) & 15u) - 4;
-                    mn = lo_q < mn ? lo_q : mn;
-                    mx = hi_q > mx ? hi_q : mx;
-                    delta += (int)(e & 15u) - 4;
-                }
+                const bool valid = nv > 0;
+                const int np = __popc(pin), nm = __popc(pout), delta = np - nm;
                 int incl = delta;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -655,40 +648,72 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                     if (lane >= (unsigned)d) incl += t;
                 }
                 const int cs = c + incl - delta;                   // count at the start of this lane's word
-                const bool valid = nv > 0;
-                const int mn0 = mn < 0 ? mn : 0, mx0 = mx > 0 ? mx : 0;
-                // levels the word visits, including the dip of a step that subtracts and adds in the same step
-                const int lo_level = cs + mn0 - (both ? 1 : 0), hi_level = cs + mx0;
+                // Levels the word can visit, first by the cheap bound [cs - #minus, cs + #plus] (a step that subtracts
+                // and adds dips one level more). The exact extremes (nibble table) are only needed by a word that
+                // might lower the epoch's minimum, raise its record level, or be flagged: decided for the whole warp.
+                int mn = -nm, mx = np;                             // lowest / highest after-step partial sum (bounds)
                 bool tz = false;
-                for (int i = 0; i < k.n_zones; ++i) tz |= lo_level <= k.zhi[i] && hi_level >= k.zlo[i];
-                int emax = -0x7FFFFFFF;                            // top of the highest edge interval that starts at or below hi_level
-                for (int i = 0; i < k.n_edges; ++i)
-                    if (k.elo[i] <= hi_level && k.ehi[i] > emax) emax = k.ehi[i];
+                {
+                    const int lo_b = cs - nm - (both ? 1 : 0), hi_b = cs + np;
+                    for (int i = 0; i < k.n_zones; ++i) tz |= lo_b <= k.zhi[i] && hi_b >= k.zlo[i];
+                    const bool want = valid && (tz || cs - nm < cmin || hi_b > trec);
+                    if (__any_sync(0xffffffffu, want)) {
+                        int d = 0;
+                        mn = 99;
+                        mx = -99;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const unsigned e = lut[((pin >> (4 * q)) & 15u) | (((pout >> (4 * q)) & 15u) << 4)];
+                            const int lo_q = d + (int)((e >> 4) & 15u) - 4, hi_q = d + (int)((e >> 8) & 15u) - 4;
+                            mn = lo_q < mn ? lo_q : mn;
+                            mx = hi_q > mx ? hi_q : mx;
+                            d += (int)(e & 15u) - 4;
+                        }
+                        const int mn0e = mn < 0 ? mn : 0, mx0e = mx > 0 ? mx : 0;
+                        tz = false;
+                        for (int i = 0; i < k.n_zones; ++i) tz |= cs + mn0e - (both ? 1 : 0) <= k.zhi[i] && cs + mx0e >= k.zlo[i];
+                    }
+                }
+                tz = tz && valid;
+                const int hi_level = cs + (mx > 0 ? mx : 0);
+                const unsigned tzmask = __ballot_sync(0xffffffffu, tz);
                 int cur = 0;
                 for (;;) {
+                    // first level whose first visit ends the epoch: beyond the anchor's binade, or inside an edge interval
+                    int H = an.c_edge + 1;
+                    for (int i = 0; i < k.n_edges; ++i)
+                        if (k.ehi[i] >= trec) {
+                            const int h = k.elo[i] > trec + 1 ? k.elo[i] : trec + 1;
+                            H = h < H ? h : H;
+                        }
                     const bool in_range = valid && (int)lane >= cur;
-                    const bool flag = in_range && (tz || (hi_level > trec && (hi_level > an.c_edge || emax >= trec)));
+                    const bool flag = in_range && (tz || hi_level >= H);
                     const unsigned fm = __ballot_sync(0xffffffffu, flag);
-                    const int first = fm ? __ffs(fm) - 1 : 32;
+                    int first = fm ? __ffs(fm) - 1 : 32;
                     const bool seg = in_range && (int)lane < first;
                     const int seg_min = __reduce_min_sync(0xffffffffu, seg ? cs + mn : 0x7FFFFFFF);
                     const int seg_max = __reduce_max_sync(0xffffffffu, seg ? hi_level : -0x7FFFFFFF);
                     cmin = seg_min < cmin ? seg_min : cmin;
                     trec = seg_max > trec ? seg_max : trec;
                     if (first == 32) break;
-                    // close the epoch, then walk the flagged word with the reference's own operations
+                    // close the epoch, then walk the flagged word -- and the tie-zone words right behind it -- with the
+                    // reference's own operations
                     const double f = kw_eval(an, k, cmin);
                     best = f < best ? f : best;
                     int cw = __shfl_sync(0xffffffffu, cs, first);
-                    const uint32_t win = __shfl_sync(0xffffffffu, in, first), wout = __shfl_sync(0xffffffffu, out, first);
                     double w = kw_eval(an, k, cw);
-                    uint32_t todo = win | wout;
-                    while (todo) {
-                        const int t = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        if ((wout >> t) & 1u) { w -= k.rq; --cw; }     // read.cpp:229 (w -= 0.0 changes nothing)
-                        if ((win >> t) & 1u) { w += k.rq; ++cw; }      // read.cpp:230
-                        best = w < best ? w : best;                    // read.cpp:231-232
+                    for (;;) {
+                        const uint32_t win = __shfl_sync(0xffffffffu, in, first), wout = __shfl_sync(0xffffffffu, out, first);
+                        uint32_t todo = win | wout;
+                        while (todo) {
+                            const int t = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            if ((wout >> t) & 1u) { w -= k.rq; --cw; }     // read.cpp:229 (w -= 0.0 changes nothing)
+                            if ((win >> t) & 1u) { w += k.rq; ++cw; }      // read.cpp:230
+                            best = w < best ? w : best;                    // read.cpp:231-232
+                        }
+                        if (first == 31 || !((tzmask >> (first + 1)) & 1u)) break;
+                        ++first;
                     }
                     kw_set_anchor(an, k, w, cw);
                     cmin = cw;

@@ -102,7 +102,9 @@ int64_t FastxReader::next() {
         if (qual.size() >= seq.size()) break;
     }
     if (qual_lines != 1) simple = false;
-    if (err_) return -3;
+    // a stream error while reading the quality string: kseq's operator precedence (kseq.h:213-216) reports it as a
+    // truncated quality string (-2, "incorrect FASTQ format"), not as -3; same here
+    if (err_) return -2;
     last_char_ = 0;
     if (seq.size() != qual.size()) return -2;
     return (int64_t)seq.size();

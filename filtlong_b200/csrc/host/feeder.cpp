@@ -291,8 +291,9 @@ struct Writer {
     static constexpr int MAXV = 1000;
     struct iovec v[MAXV];
     int nv = 0;
-    std::vector<std::string> small;            // child names: must stay alive until the flush
+    std::vector<std::string> small;            // child names: must stay alive (and in place: short strings live inside the object) until the flush
     bool failed = false;
+    Writer() { small.reserve(256); }
     void flush() {
         int done = 0;
         while (done < nv && !failed) {
@@ -386,17 +387,17 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
         n_reads += (long long)s.rec.n;
         for (size_t i = 0; i < s.rec.n; ++i) total_bases += s.rec.len[i];
     }
-    print_read_score_progress(n_reads, total_bases);
-    std::cerr << "\n";
     {
         std::string dup;
         if (find_duplicate(shards, f.base, &dup)) {
-            std::cerr << "Error: duplicate read name: " << dup << "\n";
+            std::cerr << "Error: duplicate read name: " << dup << "\n";       // main.cpp:113-116
             cleanup();
             res.exit_code = 1;
             return res;
         }
     }
+    print_read_score_progress(n_reads, total_bases);
+    std::cerr << "\n";
     mark("duplicate-name check");
     // ---- normalise, final score, target (main.cpp:136-261) ----
     {

@@ -63,14 +63,13 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
     HostArena arena(true, false, true);
     FastxReader in(filename);
     int sequence_count = 0;
-    long long base_count = 0;
+    long long base_count = 0, last_progress = 0;
     auto flush = [&]() {
         if (arena.empty()) return;
         fl_batch b = arena.batch();
         fl_ctx *c = context();
         check(c, fl_kmers_add_batch(c, &b, multi ? 1 : 0), "fl_kmers_add_batch");
         arena.clear();
-        print_hash_progress(filename, base_count);
     };
     while (in.ok() && in.next() >= 0) {           // a parse error silently ends hashing (kmers.cpp:90-94)
         ++sequence_count;
@@ -78,6 +77,10 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
         base_count += (long long)in.seq.size();
         arena.add(in.seq.data(), nullptr, (int64_t)in.seq.size());
         if (arena.padded_bases() >= kBatchBases) flush();
+        if (base_count - last_progress >= 483611) {    // the reference's progress cadence (kmers.cpp:123-126)
+            last_progress = base_count;
+            print_hash_progress(filename, base_count);
+        }
     }
     flush();
     print_hash_progress(filename, base_count);

@@ -2,6 +2,10 @@
 // same constructor signature, same public data members and methods. All scoring happens on the GPU
 // behind the C ABI; a Read object is a host-side record of the result rows.
 //
+//   Deviations from the reference's object, both invisible to main(): (1) a child's m_first_base_in_kmer /
+//   m_last_base_in_kmer are -1 (the reference's child re-runs the constructor and computes its own; nothing
+//   reads them); (2) constructing a Read scores on the Kmers' context and forgets whatever a ReadSet had
+//   pushed there: use one or the other on a given Kmers, not both.
 //   Read(name, seq, qscores, length, kmers, args)   scores ONE read synchronously (one small batch
 //       through fl_reads_push): signature-compatible, meant for callers and tests written against
 //       the reference. Throughput code uses ReadSet below, which scores a whole batch per call and
