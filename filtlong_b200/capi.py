@@ -135,6 +135,8 @@ SYMBOLS = [
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     ("fl_host_alloc", C.c_int, [C.c_uint64, C.POINTER(_P)]),
     ("fl_host_free", None, [_P]),
+    ("fl_host_register", C.c_int, [_P, C.c_uint64]),
+    ("fl_host_unregister", None, [_P]),
     ("fl_reads_push_device", C.c_int, [_P, C.POINTER(Batch)]),
     ("fl_reads_reset", C.c_int, [_P]),
     ("fl_reads_count", C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),

@@ -95,8 +95,9 @@ template <int MODE, int FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
-    const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
-    const unsigned long long pol_last = MODE == 3 ? l2_policy_evict_last() : 0ull;
+    // MODE 4: the table sectors stream through L2 once (evict_first) while the pre-filter is asked to stay (evict_last)
+    const unsigned long long pol_first = (MODE == 3 || MODE == 4) ? l2_policy_evict_first() : 0ull;
+    const unsigned long long pol_last = (MODE == 3 || MODE == 4) ? l2_policy_evict_last() : 0ull;
     (void)pol_last;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -164,7 +165,10 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         for (int t = 0; t < 5; ++t) hq[t] = hq[t + 1];
                         const uint32_t word = (mn * 0x85EBCA6Bu) >> (32 - a.filter_log2_words);
                         const bool live = half * 16 + i < nvalid;
-                        if (live && word != wprev) f[i] = __ldcg(a.filter + word);
+                        if (live && word != wprev) {
+                            if (MODE == 4) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
+                            else f[i] = __ldcg(a.filter + word);
+                        }
                         else f[i] = (live && i > 0) ? f[i > 0 ? i - 1 : 0] : 0ull;
                         wprev = live ? word : 0xFFFFFFFFu;
                     }
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         unsigned long long fb;
                         fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         if (half * 16 + i < nvalid) {
-                            if (MODE == 3) asm volatile("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
+                            if (MODE == 3 || MODE == 4) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
                             else if (a.filter_kind & 2) f[i] = __ldcg(a.filter + word);   // L2 only (no L1 line fill)
                             else f[i] = __ldg(a.filter + word);
                         } else f[i] = 0ull;
@@ -210,10 +214,16 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         const uint32_t key = (fl_kmer_at(w, p0 + 3) >> 6) & 0x3FFFFFFu;   // bases p0+3 .. p0+15
                         const bool need = p0 < nvalid && ((go >> (4 * g)) & 0xFu);
                         if (need) {
-                            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                         : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                           "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                         : "l"(table + (size_t)key * 8u));
+                            if (MODE == 4)
+                                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                             : "l"(table + (size_t)key * 8u), "l"(pol_first));
+                            else
+                                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                             : "l"(table + (size_t)key * 8u));
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
@@ -863,9 +873,11 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                 FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
             }
             const bool mini = (ctx->filter_kind & 1) != 0;      // minimizer-keyed filter words, loads de-duplicated per lane
+            const bool hinted = ctx->probe_mode == 4;             // FL_PROBE_MODE=4: L2 eviction hints (table evict_first, filter evict_last)
             if (ctx->use_anchor) {
-                if (ctx->use_filter && mini) k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa);
-                else if (ctx->use_filter) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
+                if (ctx->use_filter && mini) { if (hinted) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa); else k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa); }
+                else if (ctx->use_filter) { if (hinted) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa); else k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa); }
+                else if (hinted) k_probe_paint<4, 0, true><<<blocks, 256, 0, st>>>(pa);
                 else k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
             } else if (ctx->use_filter) {                        // plain bitmap (FL_ANCHOR=0: cross-checks and profiling)
                 if (mini) k_probe_paint<2, 2, false><<<blocks, 256, 0, st>>>(pa);

@@ -356,3 +356,16 @@ extern "C" int fl_host_alloc(uint64_t n_bytes, void **out) {
 extern "C" void fl_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
+
+// page-lock memory the caller already owns (and may already be filling): lets a reader thread start on the
+// input while the CUDA context is still coming up
+extern "C" int fl_host_register(void *p, uint64_t n_bytes) {
+    if (!p) return FL_EINVAL;
+    if (cudaHostRegister(p, (size_t)n_bytes, cudaHostRegisterPortable) == cudaSuccess) return FL_OK;
+    (void)cudaGetLastError();
+    return FL_ENOMEM;
+}
+
+extern "C" void fl_host_unregister(void *p) {
+    if (p && cudaHostUnregister(p) != cudaSuccess) (void)cudaGetLastError();
+}

@@ -128,9 +128,10 @@ struct Shard {
 };
 
 struct Ring {
-    static constexpr int K = 3;
-    char *slot[K] = {nullptr, nullptr, nullptr};
-    int state[K] = {0, 0, 0};                   // 0 free, 1 filled
+    static constexpr int K = 6;                 // slots = reader threads per shard
+    char *slot[K] = {nullptr};
+    bool registered[K] = {false};
+    int state[K] = {0};                         // 0 free, 1 filled, -1 the reader failed
     std::mutex m;
     std::condition_variable cv;
 };
@@ -139,17 +140,54 @@ void check(fl_ctx *c, int rc, const char *what) {
     if (rc != FL_OK) throw std::runtime_error(std::string(what) + ": " + fl_last_error(c));
 }
 
+// get_ctx0: the caller's context for shard 0 (creating it may take the second or so the CUDA driver needs: the
+// readers below are already filling the ring by then)
 void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, int format, const fl_params &params, int nranks,
-               const unsigned char *comm_id, fl_ctx *ctx0, std::atomic<bool> &abort_all, uint64_t max_chunk, bool share_kmers) {
+               const unsigned char *comm_id, const std::function<fl_ctx *()> &get_ctx0, std::atomic<bool> &abort_all, uint64_t slot_bytes,
+               bool share_kmers) {
     Ring ring;
-    std::vector<std::thread> copiers;
+    std::vector<std::thread> readers;
     try {
-        if (sh.index == 0) sh.ctx = ctx0;
+        // reader threads first: pread() from the page cache needs neither CUDA nor page faults on a mapping.
+        // Chunk i of the shard goes through slot i % K.
+        const size_t n_chunks = sh.chunk_hi - sh.chunk_lo;
+        for (int k = 0; k < Ring::K; ++k) {
+            void *p = nullptr;
+            if (posix_memalign(&p, 2u << 20, (size_t)slot_bytes + 4096) != 0) throw std::runtime_error("chunk ring: out of memory");
+            ring.slot[k] = (char *)p;
+        }
+        for (int k = 0; k < Ring::K; ++k)
+            readers.emplace_back([&, k] {
+                for (size_t i = (size_t)k; i < n_chunks; i += Ring::K) {
+                    {
+                        std::unique_lock<std::mutex> lk(ring.m);
+                        ring.cv.wait(lk, [&] { return ring.state[k] == 0 || abort_all.load(); });
+                        if (abort_all.load()) return;
+                    }
+                    const Chunk &c = plan[sh.chunk_lo + i];
+                    uint64_t done = 0;
+                    const uint64_t want = c.end - c.begin;
+                    bool ok = true;
+                    while (done < want) {
+                        const ssize_t r = pread(f.fd, ring.slot[k] + done, (size_t)(want - done), (off_t)(c.begin + done));
+                        if (r <= 0) { ok = false; break; }
+                        done += (uint64_t)r;
+                    }
+                    {
+                        std::lock_guard<std::mutex> lk(ring.m);
+                        ring.state[k] = ok ? 1 : -1;
+                    }
+                    ring.cv.notify_all();
+                    if (!ok) return;
+                }
+            });
+        if (sh.index == 0) sh.ctx = get_ctx0();
         else {
             if (fl_ctx_create(&params, sh.device, &sh.ctx) != FL_OK) throw std::runtime_error(std::string("fl_ctx_create: ") + fl_last_error(nullptr));
             sh.owns_ctx = true;
         }
         check(sh.ctx, fl_ctx_set_params(sh.ctx, &params), "fl_ctx_set_params");
+        for (int k = 0; k < Ring::K; ++k) ring.registered[k] = fl_host_register(ring.slot[k], slot_bytes + 4096) == FL_OK;
         if (nranks > 1) {
             check(sh.ctx, fl_comm_init(sh.ctx, comm_id, sh.index, nranks), "fl_comm_init");
             if (share_kmers) {
@@ -158,37 +196,14 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
                 check(sh.ctx, fl_kmers_finalize(sh.ctx, &nk), "fl_kmers_finalize");
             }
         }
-        for (int k = 0; k < Ring::K; ++k) {
-            void *p = nullptr;
-            if (fl_host_alloc(max_chunk + 64, &p) != FL_OK) throw std::runtime_error("pinned chunk ring: out of memory");
-            ring.slot[k] = (char *)p;
-        }
-        // copy threads: chunk i of the shard goes through slot i % K
-        const size_t n_chunks = sh.chunk_hi - sh.chunk_lo;
-        for (int k = 0; k < Ring::K; ++k)
-            copiers.emplace_back([&, k] {
-                for (size_t i = (size_t)k; i < n_chunks; i += Ring::K) {
-                    {
-                        std::unique_lock<std::mutex> lk(ring.m);
-                        ring.cv.wait(lk, [&] { return ring.state[k] == 0 || abort_all.load(); });
-                        if (abort_all.load()) return;
-                    }
-                    const Chunk &c = plan[sh.chunk_lo + i];
-                    memcpy(ring.slot[k], f.base + c.begin, (size_t)(c.end - c.begin));
-                    {
-                        std::lock_guard<std::mutex> lk(ring.m);
-                        ring.state[k] = 1;
-                    }
-                    ring.cv.notify_all();
-                }
-            });
         size_t guess = 1024;
         for (size_t i = 0; i < n_chunks && !abort_all.load(); ++i) {
             const int k = (int)(i % Ring::K);
             {
                 std::unique_lock<std::mutex> lk(ring.m);
-                ring.cv.wait(lk, [&] { return ring.state[k] == 1 || abort_all.load(); });
+                ring.cv.wait(lk, [&] { return ring.state[k] != 0 || abort_all.load(); });
                 if (abort_all.load()) break;
+                if (ring.state[k] < 0) throw std::runtime_error("Error reading the input file");
             }
             const Chunk &c = plan[sh.chunk_lo + i];
             const uint64_t nb = c.end - c.begin;
@@ -226,8 +241,11 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
         abort_all.store(true);
     }
     ring.cv.notify_all();
-    for (auto &t : copiers) t.join();
-    for (int k = 0; k < Ring::K; ++k) fl_host_free(ring.slot[k]);
+    for (auto &t : readers) t.join();
+    for (int k = 0; k < Ring::K; ++k) {
+        if (ring.registered[k]) fl_host_unregister(ring.slot[k]);
+        free(ring.slot[k]);
+    }
 }
 
 // main.cpp:169-261 on every shard (collective over NCCL when there are several), then the arrays the writer needs
@@ -330,16 +348,16 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     if (!format) return res;
     const bool kmers_empty = kmers.empty();
     if (format == FL_TEXT_FASTA && kmers_empty) return res;             // main.cpp:103-106: the host path prints the error
-    uint64_t target = 256ull << 20;
+    uint64_t target = 64ull << 20;
     if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
     if (target < (1ull << 20)) target = 1ull << 20;
-    const uint64_t max_chunk = target + (64ull << 20) > (2047ull << 20) ? (2047ull << 20) : target + (64ull << 20);
+    if (target > (1024ull << 20)) target = 1024ull << 20;
+    const uint64_t max_chunk = target;                                   // plan_chunks never cuts later than `target` bytes after a chunk's start
     int nranks = args.gpus;
     std::vector<Chunk> plan;
     if (!plan_chunks(f.base, f.size, format, target, max_chunk, plan) || plan.empty()) return res;
     if ((size_t)nranks > plan.size()) nranks = (int)plan.size();         // tiny inputs: fewer shards than GPUs asked for
 
-    fl_ctx *ctx0 = kmers.context();
     const fl_params params = params_from_arguments(args);
     unsigned char comm_id[FL_COMM_ID_BYTES] = {0};
     if (nranks > 1 && fl_comm_unique_id(comm_id) != FL_OK) throw std::runtime_error("NCCL is not available: cannot shard across GPUs");
@@ -358,12 +376,14 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
         shards.back().chunk_hi = plan.size();
     }
     std::atomic<bool> abort_all(false);
+    fl_ctx *ctx0 = nullptr;
+    const std::function<fl_ctx *()> get_ctx0 = [&]() { ctx0 = kmers.context(); return ctx0; };
     {
         std::vector<std::thread> ts;
         for (int r = 1; r < nranks; ++r)
-            ts.emplace_back(run_shard, std::ref(shards[r]), std::cref(f), std::cref(plan), format, std::cref(params), nranks, comm_id, ctx0,
-                            std::ref(abort_all), max_chunk, !kmers_empty);
-        run_shard(shards[0], f, plan, format, params, nranks, comm_id, ctx0, abort_all, max_chunk, !kmers_empty);
+            ts.emplace_back(run_shard, std::ref(shards[r]), std::cref(f), std::cref(plan), format, std::cref(params), nranks, comm_id,
+                            std::cref(get_ctx0), std::ref(abort_all), max_chunk, !kmers_empty);
+        run_shard(shards[0], f, plan, format, params, nranks, comm_id, get_ctx0, abort_all, max_chunk, !kmers_empty);
         for (auto &t : ts) t.join();
     }
     auto cleanup = [&]() {
@@ -375,7 +395,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     for (auto &s : shards)
         if (!s.error.empty()) { cleanup(); throw std::runtime_error(s.error); }
     if (abort_all.load()) {                                             // not the simple layout after all: start over on the host
-        fl_reads_reset(ctx0);
+        if (ctx0) fl_reads_reset(ctx0);
         cleanup();
         return res;
     }

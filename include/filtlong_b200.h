@@ -182,6 +182,11 @@ int fl_reads_push_text(fl_ctx *ctx, const char *host_text, uint64_t n_bytes, int
  * boundary links no CUDA runtime of its own. */
 int fl_host_alloc(uint64_t n_bytes, void **out);
 void fl_host_free(void *p);
+/* Page-locks memory the caller owns (it may already be filling it from another thread: a reader can start on
+ * the input while the CUDA context is still coming up). FL_ENOMEM if the driver refuses: the buffers still work,
+ * copies are just staged by the driver. */
+int fl_host_register(void *p, uint64_t n_bytes);
+void fl_host_unregister(void *p);
 /* Forget all scored reads (keeps the k-mer set and parameters). */
 int fl_reads_reset(fl_ctx *ctx);
 /* Number of input reads / of "reads2" rows (children replace their parent, main.cpp:138-147). */
