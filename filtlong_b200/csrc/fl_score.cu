@@ -448,30 +448,29 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
 //
 // The reference's chain:  w0 = fl(c0 / ws);  per step  w -= out ? rq : 0;  w += in ? rq : 0;  best = min(best, w),
 // rq = fl(1 / ws). With c the window's hit count (an integer prefix sum of the mask: parallel):
-//  (1) inside one binade whose grid does not put rq exactly half way between two grid points ("tie binade")
-//      adding / subtracting rq moves w by exactly R = rq rounded to the grid -- inverse operations;
+//  (1) inside one binade adding / subtracting rq moves w by exactly R = rq rounded to the binade's grid -- inverse
+//      operations. Also in a "tie binade" (rq = (n + 1/2) grid units exactly): round-half-even makes every result
+//      of an operation there EVEN, and from an even value the step is the even one of n, n + 1;
 //  (2) subtracting rq across a binade's floor (onto the finer grid) and adding it back returns to the same value;
 //  (3) hence from an ANCHOR (w_a, c_a) every value the chain takes at a level c it reaches by moves below the
-//      highest level visited so far, outside tie binades, is one function F(c): walk down from the anchor (or up,
+//      highest level visited so far is one function F(c): walk down from the anchor (or up,
 //      on the anchor's grid). The chain's minimum over such an EPOCH is F(min c): one integer reduction, one
 //      short walk (grid jumps inside a binade, one true subtraction per binade floor);
 //  (4) not reversible: an addition that reaches a level not visited since the anchor AND next to a binade edge
-//      (it enters the coarser grid above, or leaves the binade's lowest level), and anything inside a tie binade
-//      (round-half-even looks at the parity of w). A 32-step word whose count range does either is walked with
-//      the reference's own double operations and a new epoch starts from the value it produced. Rare: a few
-//      record levels per row; for ws = 250 the only tie binade is [2^-5, 2^-4), windows with 8..15 hits.
+//      (it enters the coarser grid above, or leaves the binade's lowest level), and an ODD value inside a tie
+//      binade (the first after entering from the finer grid below, or w0 itself) until an operation made it even.
+//      A 32-step word that does either is walked with the reference's own double operations and a new epoch
+//      starts from the value it produced. Rare: a few record levels per row.
 // tests/models/kmer_window_model.c is the scalar model of exactly this procedure (fuzzed against the reference
 // recurrence: tests/test_kmer_window_model.py); the kernel below is its transcription, 32 words per iteration.
 // ---------------------------------------------------------------------------------------------
-#define KW_MAX_ZONES 8
 #define KW_MAX_EDGES 16
 
 struct KwConsts {
     double rq;
     unsigned long long mant_rq;               // 53-bit significand of rq
     int e_rq;                                 // rq in [2^e_rq, 2^(e_rq+1))
-    int n_zones, n_edges;
-    int zlo[KW_MAX_ZONES], zhi[KW_MAX_ZONES]; // count intervals whose values may lie in a tie binade (+- one level)
+    int n_edges;
     int elo[KW_MAX_EDGES], ehi[KW_MAX_EDGES]; // count intervals around the binade edges 2^e / rq (+- two levels)
 };
 
@@ -480,19 +479,33 @@ struct KwAnchor {
     long long wb, rint, lo, hi;
     int c, c_edge;
     bool lattice;
+    bool unsafe;                              // odd value inside a tie binade: every differing step is walked until it is even
 };
 
-// grid parameters of the binade of w; false if it has none (rq's own binade and below -- arithmetic there is exact -- or a tie binade)
-__device__ __forceinline__ bool kw_binade(const KwConsts &k, double w, long long &wb, long long &rint, long long &lo, long long &hi) {
+// grid parameters of the binade of w; false if it has none (rq's own binade and below -- arithmetic there is exact -- or
+// an odd value in a tie binade; *tie_odd tells the latter)
+__device__ __forceinline__ bool kw_binade(const KwConsts &k, double w, long long &wb, long long &rint, long long &lo, long long &hi,
+                                          bool *tie_odd = nullptr) {
+    if (tie_odd) *tie_odd = false;
     if (!(w > 0.0)) return false;
     const long long b = __double_as_longlong(w);
     const int e = (int)((b >> 52) & 0x7FF) - 1023;
     const int s = e - k.e_rq;
     if (s < 1 || s > 52) return false;
     const unsigned long long half = 1ull << (s - 1);
-    if ((k.mant_rq & ((1ull << s) - 1ull)) == half) return false;
+    long long r = (long long)((k.mant_rq + half) >> s);
+    if ((k.mant_rq & ((1ull << s) - 1ull)) == half) {
+        // tie binade: rq = (n + 1/2) grid units; results of operations inside it are even, and from an even value the
+        // step is the even one of n, n + 1
+        if (b & 1) {
+            if (tie_odd) *tie_odd = true;
+            return false;
+        }
+        const long long n = (long long)(k.mant_rq >> s);
+        r = (n & 1) ? n + 1 : n;
+    }
     wb = b;
-    rint = (long long)((k.mant_rq + half) >> s);
+    rint = r;
     lo = (long long)(e + 1023) << 52;
     hi = lo + (1ll << 52);
     return true;
@@ -509,7 +522,7 @@ __device__ __forceinline__ long long kw_floor_div(long long x, long long y) {
 __device__ __forceinline__ void kw_set_anchor(KwAnchor &a, const KwConsts &k, double w, int c) {
     a.w = w;
     a.c = c;
-    a.lattice = kw_binade(k, w, a.wb, a.rint, a.lo, a.hi);
+    a.lattice = kw_binade(k, w, a.wb, a.rint, a.lo, a.hi, &a.unsafe);
     a.c_edge = c;                                              // no usable grid: any level above the anchor ends the epoch
     if (a.lattice) a.c_edge = c + (int)kw_floor_div(a.hi - 2 - a.wb, a.rint);
 }
@@ -662,11 +675,8 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                 // and adds dips one level more). The exact extremes (nibble table) are only needed by a word that
                 // might lower the epoch's minimum, raise its record level, or be flagged: decided for the whole warp.
                 int mn = -nm, mx = np;                             // lowest / highest after-step partial sum (bounds)
-                bool tz = false;
                 {
-                    const int lo_b = cs - nm - (both ? 1 : 0), hi_b = cs + np;
-                    for (int i = 0; i < k.n_zones; ++i) tz |= lo_b <= k.zhi[i] && hi_b >= k.zlo[i];
-                    const bool want = valid && (tz || cs - nm < cmin || hi_b > trec);
+                    const bool want = valid && (cs - nm < cmin || cs + np > trec);
                     if (__any_sync(0xffffffffu, want)) {
                         int d = 0;
                         mn = 99;
@@ -679,14 +689,10 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                             mx = hi_q > mx ? hi_q : mx;
                             d += (int)(e & 15u) - 4;
                         }
-                        const int mn0e = mn < 0 ? mn : 0, mx0e = mx > 0 ? mx : 0;
-                        tz = false;
-                        for (int i = 0; i < k.n_zones; ++i) tz |= cs + mn0e - (both ? 1 : 0) <= k.zhi[i] && cs + mx0e >= k.zlo[i];
                     }
                 }
-                tz = tz && valid;
                 const int hi_level = cs + (mx > 0 ? mx : 0);
-                const unsigned tzmask = __ballot_sync(0xffffffffu, tz);
+                const bool differs = valid && (in | out) != 0u;
                 int cur = 0;
                 for (;;) {
                     // first level whose first visit ends the epoch: beyond the anchor's binade, or inside an edge interval
@@ -697,7 +703,7 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                             H = h < H ? h : H;
                         }
                     const bool in_range = valid && (int)lane >= cur;
-                    const bool flag = in_range && (tz || hi_level >= H);
+                    const bool flag = in_range && ((an.unsafe && differs) || hi_level >= H);
                     const unsigned fm = __ballot_sync(0xffffffffu, flag);
                     int first = fm ? __ffs(fm) - 1 : 32;
                     const bool seg = in_range && (int)lane < first;
@@ -706,13 +712,12 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                     cmin = seg_min < cmin ? seg_min : cmin;
                     trec = seg_max > trec ? seg_max : trec;
                     if (first == 32) break;
-                    // close the epoch, then walk the flagged word -- and the tie-zone words right behind it -- with the
-                    // reference's own operations
+                    // close the epoch, then walk the flagged word with the reference's own operations
                     const double f = kw_eval(an, k, cmin);
                     best = f < best ? f : best;
                     int cw = __shfl_sync(0xffffffffu, cs, first);
                     double w = kw_eval(an, k, cw);
-                    for (;;) {
+                    {
                         const uint32_t win = __shfl_sync(0xffffffffu, in, first), wout = __shfl_sync(0xffffffffu, out, first);
                         uint32_t todo = win | wout;
                         while (todo) {
@@ -722,8 +727,6 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
                             if ((win >> t) & 1u) { w += k.rq; ++cw; }      // read.cpp:230
                             best = w < best ? w : best;                    // read.cpp:231-232
                         }
-                        if (first == 31 || !((tzmask >> (first + 1)) & 1u)) break;
-                        ++first;
                     }
                     kw_set_anchor(an, k, w, cw);
                     cmin = cw;
@@ -812,26 +815,6 @@ static void kw_make_consts(int ws, KwConsts *k) {
         k->elo[k->n_edges] = (int)floor(x) - 2;
         k->ehi[k->n_edges] = (int)ceil(x) + 2;
         k->n_edges++;
-    }
-    for (int s = 1; s <= 52 && k->e_rq + s <= 1; ++s) {
-        if ((k->mant_rq & ((1ull << s) - 1ull)) != (1ull << (s - 1))) continue;
-        // tie binade [2^e, 2^(e+1)), e = e_rq + s: levels c with c * rq inside it, +- 1e-9 relative for the chain's
-        // drift, +- one level so that every operation with an end inside the binade lies inside the zone
-        const double lo = ldexp(1.0, k->e_rq + s), hi = ldexp(1.0, k->e_rq + s + 1);
-        int zl = (int)floor(lo * (1.0 - 1e-9) * (double)ws) - 1;
-        const int zh = (int)ceil(hi * (1.0 + 1e-9) * (double)ws) + 1;
-        if (zl < 0) zl = 0;
-        if (zl > ws) continue;
-        if (k->n_zones < KW_MAX_ZONES) {
-            k->zlo[k->n_zones] = zl;
-            k->zhi[k->n_zones] = zh;
-            k->n_zones++;
-        } else {                                                    // too many: one zone covering everything (every word is walked)
-            k->n_zones = 1;
-            k->zlo[0] = 0;
-            k->zhi[0] = 0x7FFFFFFF;
-            return;
-        }
     }
 }
 

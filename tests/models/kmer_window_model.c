@@ -6,21 +6,22 @@
  * with rq = fl(1 / ws), started from w0 = fl(c0 / ws). Let c be the window's hit count (an integer prefix
  * sum of the mask: parallel). Facts used (IEEE-754 round to nearest even; "grid" of a binade = its ulp):
  *
- *  (1) inside one binade whose grid does not put rq exactly half way between two grid points ("tie binade"),
- *      adding / subtracting rq moves w by exactly R = rq rounded to the grid: the two are inverse;
+ *  (1) inside one binade adding / subtracting rq moves w by exactly R = rq rounded to the binade's grid: the two
+ *      are inverse. Also in a "tie binade" (rq = (n + 1/2) grid units exactly): round-half-even makes every result
+ *      of an operation there EVEN, and from an even value the step is the even one of n, n + 1;
  *  (2) subtracting rq across a binade edge (the lower grid is finer, w is on it) and adding it back returns
  *      to the same value (the two roundings compose to the identity whatever the parity: see DESIGN.md);
  *  (3) so, starting from an ANCHOR (w_a, c_a), every value the chain takes at a level c that is reached by
- *      moves BELOW the anchor's binade ceiling, and outside tie binades, is one fixed function F(c): the
+ *      moves BELOW the highest level visited since the anchor is one fixed function F(c): the
  *      value obtained by walking from the anchor down (or up, inside the anchor's binade) to c. The chain's
  *      minimum over such a stretch ("epoch") is F(min c) -- one count reduction and one short walk;
  *  (4) what is NOT reversible: an addition that takes the chain to a level it has not visited since the anchor
  *      AND sits next to a binade edge -- it either carries w into the coarser grid above (which forgets the
  *      low bit) or leaves the binade's lowest level (the subtraction that would undo it falls through the
- *      floor onto the finer grid); a new epoch starts from the value it produced. And anything inside a tie
- *      binade (rounding depends on the parity of w). Words of 32 steps whose count range does either are
- *      walked with true double operations; they are rare (a handful of record levels per row; for ws = 250
- *      the only tie binade is [2^-5, 2^-4): windows with 8..15 hits).
+ *      floor onto the finer grid); a new epoch starts from the value it produced. And an ODD value inside a tie
+ *      binade (the first one after entering from the finer grid below, or w0 itself): nothing is reversible
+ *      until an operation has made it even. Words of 32 steps that do either are walked with true double
+ *      operations; they are rare (a handful of record levels per row).
  *
  * The model processes a row in words of 32 steps exactly like one lane of the kernel does (word statistics
  * from a nibble look-up table, a predicate that flags the word, a scalar walk only if flagged), so that the
@@ -30,14 +31,10 @@
 #include <stdint.h>
 #include <string.h>
 
-#define KW_MAX_ZONES 8
-
 typedef struct {
     double rq;
     int e_rq;             /* rq in [2^e_rq, 2^(e_rq+1)) */
     uint64_t mant_rq;     /* 53-bit significand of rq */
-    int n_zones;          /* count intervals [zlo, zhi] whose values may lie in a tie binade (one level of margin) */
-    int zlo[KW_MAX_ZONES], zhi[KW_MAX_ZONES];
     int n_edges;          /* count intervals around the binade edges 2^e / rq (two levels of margin) */
     int elo[16], ehi[16];
 } chain_consts;
@@ -48,6 +45,7 @@ typedef struct {
     int lattice;          /* anchor's binade has a usable grid (above rq's own binade, not a tie binade) */
     int64_t wb, rint, lo, hi;
     int c_edge;           /* highest level reachable from the anchor without leaving its binade upwards (conservative) */
+    int unsafe;           /* odd value inside a tie binade: nothing is reversible until an operation made it even */
 } anchor_t;
 
 static inline int64_t d2b(double x) { int64_t b; memcpy(&b, &x, 8); return b; }
@@ -58,7 +56,6 @@ void kw_consts(chain_consts *k, int ws) {
     const int64_t b = d2b(k->rq);
     k->e_rq = (int)((b >> 52) & 0x7FF) - 1023;
     k->mant_rq = ((uint64_t)b & ((1ull << 52) - 1ull)) | (1ull << 52);
-    k->n_zones = 0;
     k->n_edges = 0;
     for (int e = k->e_rq; e <= 1 && k->n_edges < 16; ++e) {           /* edges 2^e for every binade a count 0..ws can reach */
         const double x = ldexp(1.0, e) * (double)ws;
@@ -67,29 +64,6 @@ void kw_consts(chain_consts *k, int ws) {
         k->ehi[k->n_edges] = (int)ceil(x) + 2;
         k->n_edges++;
     }
-    for (int s = 1; s <= 52 && k->e_rq + s <= 1; ++s) {
-        if ((k->mant_rq & ((1ull << s) - 1ull)) != (1ull << (s - 1))) continue;
-        /* tie binade [2^e, 2^(e+1)), e = e_rq + s: levels c with c * rq within it, +- a relative 1e-9 for the
-         * drift of the chain, +- one level so that every operation with an end inside the binade is inside the zone */
-        const double lo = ldexp(1.0, k->e_rq + s), hi = ldexp(1.0, k->e_rq + s + 1);
-        int zl = (int)floor(lo * (1.0 - 1e-9) * (double)ws) - 1, zh = (int)ceil(hi * (1.0 + 1e-9) * (double)ws) + 1;
-        if (zl < 0) zl = 0;
-        if (zl > ws) continue;
-        if (k->n_zones < KW_MAX_ZONES) {
-            k->zlo[k->n_zones] = zl;
-            k->zhi[k->n_zones] = zh;
-            k->n_zones++;
-        } else {                      /* too many: one zone covering everything (every word walks) */
-            k->n_zones = 1; k->zlo[0] = 0; k->zhi[0] = 0x7FFFFFFF;
-            return;
-        }
-    }
-}
-
-static inline int touches_zone(const chain_consts *k, int lo, int hi) {
-    for (int i = 0; i < k->n_zones; ++i)
-        if (lo <= k->zhi[i] && hi >= k->zlo[i]) return 1;
-    return 0;
 }
 
 static inline int touches_edge(const chain_consts *k, int lo, int hi) {
@@ -106,9 +80,17 @@ static int binade_of(const chain_consts *k, double w, int64_t *wb, int64_t *rint
     const int s = e - k->e_rq;
     if (s < 1 || s > 52) return 0;
     const uint64_t half = 1ull << (s - 1);
-    if ((k->mant_rq & ((1ull << s) - 1ull)) == half) return 0;      /* tie binade (only met inside a zone) */
+    int64_t r = (int64_t)((k->mant_rq + half) >> s);
+    if ((k->mant_rq & ((1ull << s) - 1ull)) == half) {
+        /* tie binade: rq = (n + 1/2) grid units. Round-half-even makes every result of an operation inside the binade
+         * EVEN, and from an even value adding / subtracting rq moves by the even one of n, n + 1: a lattice again.
+         * An odd value (only the first one after entering from the finer grid below, or the initial w0) has none. */
+        if (b & 1) return 0;
+        const int64_t n = (int64_t)(k->mant_rq >> s);
+        r = (n & 1) ? n + 1 : n;
+    }
     *wb = b;
-    *rint = (int64_t)((k->mant_rq + half) >> s);
+    *rint = r;
     *lo = (int64_t)(e + 1023) << 52;
     *hi = *lo + (1ll << 52);
     return 1;
@@ -118,6 +100,12 @@ static void set_anchor(anchor_t *a, const chain_consts *k, double w, int c) {
     a->w = w;
     a->c = c;
     a->lattice = binade_of(k, w, &a->wb, &a->rint, &a->lo, &a->hi);
+    a->unsafe = 0;
+    if (!a->lattice && w > 0.0) {
+        const int64_t b = d2b(w);
+        const int s = (int)((b >> 52) & 0x7FF) - 1023 - k->e_rq;
+        if (s >= 1 && s <= 52 && (k->mant_rq & ((1ull << s) - 1ull)) == (1ull << (s - 1))) a->unsafe = 1;
+    }
     a->c_edge = c;                                                   /* no usable grid: any level above the anchor ends the epoch */
     if (a->lattice) a->c_edge = c + (int)((a->hi - 2 - a->wb) / a->rint);
 }
@@ -211,7 +199,7 @@ double kmer_window_model(const uint32_t *mask, int S, int E, int ws, long long *
         const int mn0 = mn < 0 ? mn : 0, mx0 = mx > 0 ? mx : 0;
         /* levels the word visits, including the dip of a step that subtracts and adds in the same step */
         const int lo_level = c + mn0 - (both ? 1 : 0), hi_level = c + mx0;
-        const int flagged = touches_zone(&k, lo_level, hi_level) ||
+        const int flagged = (a.unsafe && (in | out)) ||
                             (hi_level > trec && (hi_level > a.c_edge || touches_edge(&k, trec, hi_level)));
         if (!flagged) {
             if (c + mn < cmin) cmin = c + mn;
