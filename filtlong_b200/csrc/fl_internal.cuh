@@ -117,7 +117,7 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    int filter_kind = 2;                 // bit 0: word from the k-mer's minimizer (loads de-duplicated per lane) instead of a plain hash; bit 1: ld.global.cg (FL_FILTER_KIND)
+    int filter_kind = 2;                 // bit 1: load the filter with ld.global.cg (FL_FILTER_KIND); bit 0 (minimizer-keyed words) is a build-side experiment only
     bool use_filter = false;
     uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
     bool use_anchor = false;

@@ -95,9 +95,8 @@ template <int MODE, int FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
-    // MODE 4: the table sectors stream through L2 once (evict_first) while the pre-filter is asked to stay (evict_last)
-    const unsigned long long pol_first = (MODE == 3 || MODE == 4) ? l2_policy_evict_first() : 0ull;
-    const unsigned long long pol_last = (MODE == 3 || MODE == 4) ? l2_policy_evict_last() : 0ull;
+    const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
+    const unsigned long long pol_last = MODE == 3 ? l2_policy_evict_last() : 0ull;
     (void)pol_last;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -140,47 +139,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
                 uint32_t go = 0xFFFFu;                // which of the 16 k-mers still need the exact bitmap
-                if (FILT == 2) {
-                    // Pre-filter keyed by the 16-mer's MINIMIZER (smallest hashed 11-mer of its six, fl_filter_slot
-                    // kind 1): consecutive 16-mers of a lane mostly share it, and a lane only issues a load when the
-                    // word CHANGES (~1 in 3.5): the probe was bound by the L1TEX sector-request rate of one random
-                    // 8-byte load per 16-mer (ncu: L1TEX 86 %), not by bytes. The hashed 11-mers slide along the
-                    // lane's run, so each 16-mer costs one new hash and a 6-way minimum.
-                    unsigned long long f[16];
-                    uint32_t hq[6];                      // hashed 11-mers at run positions q-5 .. q
-                    auto h11 = [&](int q) -> uint32_t {  // 11-mer starting at base q (0..37) of the lane's 48 loaded bases
-                        const uint32_t x = q < 16 ? __funnelshift_l(w.w1, w.w0, 2 * q) : (q < 32 ? __funnelshift_l(w.w2, w.w1, 2 * (q - 16)) : (w.w2 << (2 * (q - 32))));
-                        return (x >> 10) * 0x9E3779B1u;
-                    };
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) hq[t] = h11(half * 16 + t);
-                    uint32_t wprev = 0xFFFFFFFFu;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        hq[5] = h11(half * 16 + i + 5);
-                        uint32_t mn = hq[0];
-#pragma unroll
-                        for (int t = 1; t < 6; ++t) mn = hq[t] < mn ? hq[t] : mn;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) hq[t] = hq[t + 1];
-                        const uint32_t word = (mn * 0x85EBCA6Bu) >> (32 - a.filter_log2_words);
-                        const bool live = half * 16 + i < nvalid;
-                        if (live && word != wprev) {
-                            if (MODE == 4) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
-                            else f[i] = __ldcg(a.filter + word);
-                        }
-                        else f[i] = (live && i > 0) ? f[i > 0 ? i - 1 : 0] : 0ull;
-                        wprev = live ? word : 0xFFFFFFFFu;
-                    }
-                    go = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t kk = fl_kmer_at(w, half * 16 + i);
-                        const uint32_t h2 = (kk ^ (kk >> 15)) * 0x85EBCA6Bu;
-                        const unsigned long long fb = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
-                        go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
-                    }
-                } else if (FILT) {
+                if (FILT) {
                     // 16 independent loads from the 32 MiB pre-filter (kept in L2): most k-mers of a
                     // noisy read are absent and stop here, without touching HBM
                     unsigned long long f[16];
@@ -190,7 +149,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         unsigned long long fb;
                         fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         if (half * 16 + i < nvalid) {
-                            if (MODE == 3 || MODE == 4) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
+                            if (MODE == 3) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
                             else if (a.filter_kind & 2) f[i] = __ldcg(a.filter + word);   // L2 only (no L1 line fill)
                             else f[i] = __ldg(a.filter + word);
                         } else f[i] = 0ull;
@@ -214,16 +173,10 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         const uint32_t key = (fl_kmer_at(w, p0 + 3) >> 6) & 0x3FFFFFFu;   // bases p0+3 .. p0+15
                         const bool need = p0 < nvalid && ((go >> (4 * g)) & 0xFu);
                         if (need) {
-                            if (MODE == 4)
-                                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                             : "l"(table + (size_t)key * 8u), "l"(pol_first));
-                            else
-                                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                             : "l"(table + (size_t)key * 8u));
+                            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                           "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                         : "l"(table + (size_t)key * 8u));
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
@@ -345,6 +298,13 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
             const uint32_t x = wi < n_words ? __ldg(m + wi) : 0u;
             const unsigned nz = __ballot_sync(0xffffffffu, x != 0u);
             const int tzc = x ? __clz(x) : 32, lzc = x ? __ffs(x) - 1 : 32;
+            // common case: every word of the step has a hit, nothing open from before can reach --split, and this is
+            // not the step that holds the read's first hit: no bad range can start or end here
+            if (seen_one && nz == 0xffffffffu && (!split_set || (split >= 64 && carry_open + 32 < split))) {
+                carry_open = __shfl_sync(0xffffffffu, tzc, 31);
+                last = (wb + 31) * 32 + 32 - carry_open;
+                continue;
+            }
             const unsigned lo_nz = nz & lower;
             const int j = lo_nz ? 31 - __clz(lo_nz) : 0;
             const int tz_j = __shfl_sync(0xffffffffu, tzc, j);
@@ -855,16 +815,14 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                 attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
                 FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
             }
-            const bool mini = (ctx->filter_kind & 1) != 0;      // minimizer-keyed filter words, loads de-duplicated per lane
-            const bool hinted = ctx->probe_mode == 4;             // FL_PROBE_MODE=4: L2 eviction hints (table evict_first, filter evict_last)
+            // Measured and dropped (profiles/r02_probe_filter_experiments.md): a minimizer-keyed pre-filter with per-lane load
+            // de-duplication (L1TEX 83 % -> 31 %, but 5x the false positives and the filter falls out of L2: 128 ms against
+            // 94 ms), L2 eviction hints and the persisting-L2 window on either flavour (+4..8 ms).
             if (ctx->use_anchor) {
-                if (ctx->use_filter && mini) { if (hinted) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa); else k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa); }
-                else if (ctx->use_filter) { if (hinted) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa); else k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa); }
-                else if (hinted) k_probe_paint<4, 0, true><<<blocks, 256, 0, st>>>(pa);
+                if (ctx->use_filter) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
                 else k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
             } else if (ctx->use_filter) {                        // plain bitmap (FL_ANCHOR=0: cross-checks and profiling)
-                if (mini) k_probe_paint<2, 2, false><<<blocks, 256, 0, st>>>(pa);
-                else k_probe_paint<2, 1, false><<<blocks, 256, 0, st>>>(pa);
+                k_probe_paint<2, 1, false><<<blocks, 256, 0, st>>>(pa);
             } else {
                 k_probe_paint<2, 0, false><<<blocks, 256, 0, st>>>(pa);
             }

@@ -128,7 +128,7 @@ struct Shard {
 };
 
 struct Ring {
-    static constexpr int K = 6;                 // slots = reader threads per shard
+    static constexpr int K = 8;                 // slots = reader threads per shard
     char *slot[K] = {nullptr};
     bool registered[K] = {false};
     int state[K] = {0};                         // 0 free, 1 filled, -1 the reader failed
@@ -348,7 +348,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     if (!format) return res;
     const bool kmers_empty = kmers.empty();
     if (format == FL_TEXT_FASTA && kmers_empty) return res;             // main.cpp:103-106: the host path prints the error
-    uint64_t target = 64ull << 20;
+    uint64_t target = 128ull << 20;
     if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
     if (target < (1ull << 20)) target = 1ull << 20;
     if (target > (1024ull << 20)) target = 1024ull << 20;
