@@ -139,7 +139,7 @@ struct fl_ctx {
     unsigned long long tie_many = 0;        // bit e: more than one table value ties there
     unsigned char tie_char[64] = {0};       // the one that does, when exactly one
     unsigned long long tie_binades_a = 0;   // bit e: some window-table value ties when w is in [2^-e, 2^(1-e))
-    int phred_mode = 2;                     // 2: k_phred_sum + k_phred_win (default: measured faster); 1: k_phred_score, both fused in one pass; 0: work-item kernels (FL_PHRED_MODE)
+    int phred_mode = 1;                     // 1: k_phred_sum + k_phred_win (default); 0: work-item kernels (FL_PHRED_MODE)
     int phred_occupancy = 0;                // blocks per SM launched for the Phred kernels, 0 = the kernel's own default (FL_PHRED_OCC)
     int lut_window = -1;
     bool phred_attr_set = false, phred_items_attr_set = false;   // cudaFuncSetAttribute is per DEVICE: kept per context

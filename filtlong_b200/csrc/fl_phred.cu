@@ -850,259 +850,6 @@ __global__ void __launch_bounds__(PT_THREADS, 4) k_phred_win(PhredArgs a) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// k_phred_score<K>: k_phred_sum and k_phred_win in ONE pass over the qualities. Same exact lattice
-// arithmetic as the two kernels above (whose comments carry the argument); what changes is the traversal:
-// the step is one window length (bases [ws + t ws, ws + (t+1) ws)), lane l owns K = ceil(ws / 32) consecutive
-// bases of it, and every base costs ONE 16-byte shared-memory gather {q[c], a_grid[c]} (8 lane-private copies:
-// conflict free for the quarter-warps of an LDS.128) that feeds both chains:
-//     acc += q                       the mean's sum on the grid of its binade (collected by budget, crossings
-//                                    resolved exactly, ties / odd bytes walked by lane 0: as in k_phred_sum)
-//     x += a_new - a_old;  min       the window chain relative to the anchor 0.75 (as in k_phred_win)
-// The quality string is read once (43 -> 20 GB of DRAM traffic on config 2) and the byte extraction, the
-// address arithmetic and the per-step loads / alignment are shared.
-// ---------------------------------------------------------------------------------------------
-#define PF_SMEM (256 * 8 * 16)         // {q, a_grid} x 8 lane-private copies = 32 KiB
-
-__device__ __forceinline__ const double2 *entry2_of(const double2 *tl, uint32_t w, int k) {
-    const uint32_t c = __byte_perm(w, 0u, 0x4440u + (unsigned)k);
-    return reinterpret_cast<const double2 *>(reinterpret_cast<const unsigned char *>(tl) + (c << 7));
-}
-
-template <int K>
-__global__ void __launch_bounds__(PT_THREADS, 3) k_phred_score(PhredArgs a, TieInfo tie) {
-    constexpr int NW = (K + 3) / 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double2 *tab = reinterpret_cast<double2 *>(smem_raw);              // [256][8] {q, a on the grid 2^-53}
-    __shared__ double s_amax;
-    __shared__ uint32_t s_mask[32][4];
-    __shared__ TieInfo s_tie;
-    const int ws = a.p.window_size;
-    const double qnan = __longlong_as_double(0x7FF8000000000000ll);
-    if (threadIdx.x == 0) {
-        s_tie = tie;
-        double mx = 0.0;
-        for (int c = 0; c < 256; ++c) {
-            const double v = a.lut[256 + c];
-            if (v >= 0.0 && v > mx && v * (double)ws <= 1.0 - 1e-10) mx = v;
-        }
-        s_amax = (0.5 + mx) - 0.5;                                     // on the grid
-    }
-    if (threadIdx.x < 32) {
-        // bytes beyond the lane's share read as '!' (q = 0, a = 0: no effect on either chain)
-        const int nb = max(0, min(K, ws - K * (int)threadIdx.x));
-        for (int i = 0; i < 2; ++i) {
-            uint32_t m = 0;
-            for (int b = 0; b < 4; ++b)
-                if (4 * i + b < nb) m |= 0xFFu << (8 * b);
-            s_mask[threadIdx.x][i] = m;
-            s_mask[threadIdx.x][2 + i] = 0x21212121u & ~m;
-        }
-    }
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-        const int c = i >> 3;
-        const double q = a.lut[c];
-        double v = a.lut[256 + c];
-        bool ok = v >= 0.0 && v * (double)ws <= 1.0 - 1e-10;
-        if (ok && v > 0.0) {
-            const double sc = ldexp(v, 53);                           // exact; v < 1 so sc < 2^53
-            ok = (sc - floor(sc)) != 0.5;                              // would tie on the grid of [0.5, 1)
-        }
-        tab[i] = make_double2((q >= 0.0 && q < 1.0) ? q : qnan, ok ? (0.5 + v) - 0.5 : qnan);
-    }
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31;
-    const double2 *tl = tab + (lane & 7);
-    const double thr = 0.5 + 2.0 * s_amax;
-    const int nb_lane = max(0, min(K, ws - K * (int)lane));           // bases of a full step owned by this lane
-    const int lpos = K * (int)lane;
-    constexpr int STEP_SHIFT = K == 2 ? 6 : (K == 4 ? 7 : 8);          // a step adds at most 32 K <= 2^STEP_SHIFT to the sum
-    uint32_t keep[NW], fill[NW];
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        keep[i] = s_mask[lane][i];
-        fill[i] = s_mask[lane][2 + i];
-    }
-    for (;;) {
-        unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(a.work + 1, 1ull);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= a.n) break;
-        const uint32_t r = a.order[it];
-        const int L = a.len[r];
-        if (L <= ws) continue;                                         // finished by k_phred_first
-        const uint8_t *q = a.qual + a.off[r];
-        const uint32_t *q32 = reinterpret_cast<const uint32_t *>(q);
-        const int maxword = (((L + 63) & ~63) >> 2) - 1;
-        // ---- the window chain's state (k_phred_win) ----
-        const double W0 = a.it_b[r];                                   // fl(sum of the first window / ws), read.cpp:223
-        bool reject = !(W0 >= thr && W0 < 1.0);
-        long long Wb = __double_as_longlong(W0), mnb = Wb;
-        bool nanf = false;
-        // ---- the mean's state (k_phred_sum): the sum of the first ws bases comes from k_phred_first ----
-        const double s0 = a.it_a[r];
-        long long sb = __double_as_longlong(s0);                       // bit pattern of the collected part of the sum
-        int e = exponent_of(s0);
-        double Cs = pow2(e), acc = Cs;
-        int budget = 0;
-        bool tieflag = e >= 0 && e < 64 && ((s_tie.any >> e) & 1ull);
-        bool snan = false;
-        double va[K], vb[K];
-        {
-            uint32_t raw[NW + 1], cw[NW];
-            load_raw<NW>(q32, lpos, maxword, raw);
-            align_raw<NW>(raw, lpos, cw);
-#pragma unroll
-            for (int k = 0; k < K; ++k) va[k] = (k < nb_lane) ? entry2_of(tl, cw[k >> 2], k & 3)->y : 0.0;
-        }
-        uint32_t pre[NW + 1];
-        load_raw<NW>(q32, ws + lpos, maxword, pre);
-        int j = ws;
-        // one step: bases [j, j + ws) (fewer in the last one)
-#define PF_STEP(WAS, NOW)                                                                                             \
-        {                                                                                                             \
-            uint32_t cw[NW];                                                                                          \
-            align_raw<NW>(pre, j + lpos, cw);                                                                         \
-            if (j + ws < L) load_raw<NW>(q32, j + ws + lpos, maxword, pre);                                           \
-            const int n = (L - j < ws) ? L - j : ws;                                                                  \
-            const int nvalid = max(0, min(nb_lane, n - lpos));                                                        \
-            _Pragma("unroll") for (int i = 0; i < NW; ++i) {                                                          \
-                uint32_t kp = keep[i];                                                                                \
-                if (n < ws) {                                                                                         \
-                    const int vb_ = nvalid - 4 * i;                                                                   \
-                    kp = vb_ >= 4 ? 0xFFFFFFFFu : (vb_ <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * vb_)));                  \
-                }                                                                                                     \
-                cw[i] = (cw[i] & kp) | (0x21212121u & ~kp);                                                           \
-            }                                                                                                         \
-            /* ---- the sum: when must the lanes' parts be collected? (k_phred_sum) ---- */                         \
-            const bool in_range = e >= 5 && e < 52;                                                                   \
-            int mode = 0;                                                                                             \
-            if (budget == 0 || tieflag) {                                                                             \
-                if (budget == 0) {                                                                                    \
-                    snan |= (acc != acc);                                                                             \
-                    sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));                          \
-                    acc = Cs;                                                                                         \
-                    if (in_range) {                                                                                   \
-                        long long room = ((__double_as_longlong(Cs) + (1ll << 52)) - sb) >> (52 - e);                 \
-                        if (room > (1ll << 30)) room = 1ll << 30;                                                     \
-                        budget = room >= 1 ? (int)((room - 1) >> STEP_SHIFT) : 0;                                     \
-                    }                                                                                                 \
-                }                                                                                                     \
-                if (!in_range || sb <= 0) {                                                                           \
-                    mode = 2;                                                                                         \
-                } else {                                                                                              \
-                    if (tieflag && (((s_tie.many >> e) & 1ull) || __any_sync(0xffffffffu, chunk_has<NW>(cw, s_tie.ch[e])))) mode = 2; \
-                    if (mode == 2 && budget > 0) {                                                                    \
-                        sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));                      \
-                        acc = Cs;                                                                                     \
-                        budget = 0;                                                                                   \
-                    }                                                                                                 \
-                    if (mode == 0 && budget == 0) mode = 1;                                                           \
-                }                                                                                                     \
-            }                                                                                                         \
-            /* ---- both chains, one gather per base ---- */                                                          \
-            double x = PT_ANCHOR, m = PT_ANCHOR;                                                                      \
-            _Pragma("unroll") for (int k = 0; k < K; ++k) {                                                           \
-                const double2 qa = *entry2_of(tl, cw[k >> 2], k & 3);                                                 \
-                acc += qa.x;                       /* read.cpp:210-211 on the grid of [Cs, 2 Cs) */                   \
-                NOW[k] = qa.y;                                                                                        \
-                if (n >= ws || k < nvalid) {                                                                          \
-                    x += NOW[k] - WAS[k];          /* read.cpp:229-230: grid multiples, the difference is exact */    \
-                    m = x < m ? x : m;             /* read.cpp:231-232 */                                             \
-                }                                                                                                     \
-            }                                                                                                         \
-            nanf |= (x != x);                                                                                         \
-            {                                                                                                         \
-                const long long nx = __double_as_longlong(x) - PT_ANCHOR_BITS;                                        \
-                const long long inc = warp_incl_scan_ll(nx, lane);                                                    \
-                const long long cand = Wb + (inc - nx) + (__double_as_longlong(m) - PT_ANCHOR_BITS);                  \
-                mnb = cand < mnb ? cand : mnb;                                                                        \
-                Wb += __shfl_sync(0xffffffffu, inc, 31);                                                              \
-            }                                                                                                         \
-            /* ---- the sum: resolve a step that may leave the binade (k_phred_sum) ---- */                         \
-            if (mode == 0) {                                                                                          \
-                --budget;                                                                                             \
-            } else {                                                                                                  \
-                bool serial = mode == 2 || __any_sync(0xffffffffu, acc != acc);                                       \
-                if (!serial) {                                                                                        \
-                    long long cur = sb;                                                                               \
-                    int ce = e, lo = 0;                                                                               \
-                    double C = Cs, part = acc;                                                                        \
-                    for (int round = 0; round < 6; ++round) {                                                         \
-                        const long long top = __double_as_longlong(C) + (1ll << 52);                                  \
-                        const long long u = (int)lane >= lo ? __double_as_longlong(part) - __double_as_longlong(C) : 0ll; \
-                        const long long P = warp_incl_scan_ll(u, lane);                                               \
-                        const unsigned cross = __ballot_sync(0xffffffffu, cur + P >= top);                            \
-                        if (cross == 0u) {                                                                            \
-                            sb = cur + __shfl_sync(0xffffffffu, P, 31);                                               \
-                            e = ce;                                                                                   \
-                            Cs = C;                                                                                   \
-                            break;                                                                                    \
-                        }                                                                                             \
-                        const int lx = __ffs(cross) - 1;                                                              \
-                        const double t0 = __longlong_as_double(cur + __shfl_sync(0xffffffffu, P - u, lx));            \
-                        C = C + C;                                                                                    \
-                        ce += 1;                                                                                      \
-                        double v = (int)lane == lx ? t0 : C;                                                          \
-                        if ((int)lane >= lx) {                                                                        \
-                            _Pragma("unroll") for (int k = 0; k < K; ++k) v += entry2_of(tl, cw[k >> 2], k & 3)->x;   \
-                        }                                                                                             \
-                        const double t = shfl_d(v, lx);                                                               \
-                        bool hit = false;                                                                             \
-                        if ((s_tie.any >> ce) & 1ull) hit = ((s_tie.many >> ce) & 1ull) || __any_sync(0xffffffffu, chunk_has<NW>(cw, s_tie.ch[ce])); \
-                        if (hit || exponent_of(t) != ce || !(t == t) || round == 5) {                                 \
-                            serial = true;                                                                            \
-                            break;                                                                                    \
-                        }                                                                                             \
-                        cur = __double_as_longlong(t);                                                                \
-                        lo = lx + 1;                                                                                  \
-                        part = v;                                                                                     \
-                    }                                                                                                 \
-                    if (!serial) tieflag = (s_tie.any >> e) & 1ull;                                                   \
-                }                                                                                                     \
-                if (serial) {                          /* the reference's own loop for this step */                   \
-                    double v = __longlong_as_double(sb);                                                              \
-                    if (lane == 0)                                                                                    \
-                        for (int p = 0; p < n; ++p) v += __ldg(a.lut + (unsigned)q[j + p]);                           \
-                    v = shfl_d(v, 0);                                                                                 \
-                    sb = __double_as_longlong(v);                                                                     \
-                    e = exponent_of(v);                                                                               \
-                    Cs = pow2(e);                                                                                     \
-                    tieflag = e >= 0 && e < 64 && ((s_tie.any >> e) & 1ull);                                          \
-                }                                                                                                     \
-                acc = Cs;                                                                                             \
-                budget = 0;                                                                                           \
-            }                                                                                                         \
-            j += ws;                                                                                                  \
-        }
-        while (true) {
-            PF_STEP(va, vb)
-            if (j >= L) break;
-            PF_STEP(vb, va)
-            if (j >= L) break;
-        }
-#undef PF_STEP
-        snan |= (acc != acc);
-        sb += warp_sum_ll(__double_as_longlong(acc) - __double_as_longlong(Cs));
-        const bool any_snan = __any_sync(0xffffffffu, snan);
-        const double s = __longlong_as_double(sb);
-        double mn = 0.0;
-        if (!reject) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const long long t = __shfl_xor_sync(0xffffffffu, mnb, o);
-                mnb = t < mnb ? t : mnb;
-            }
-            mn = __longlong_as_double(mnb);
-            reject = __any_sync(0xffffffffu, nanf) || !(mn >= thr) || any_snan || !(s == s);
-        }
-        if (lane == 0) {
-            if (reject) a.fallback[1 + atomicAdd(a.fallback, 1u)] = r;
-            else finish(a, r, L, s, mn);
-        }
-    }
-}
-
 }  // namespace
 
 static int ensure_lut(fl_ctx *ctx) {
@@ -1152,8 +899,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
     FL_TRY(fl_reserve_reads(ctx, ctx->n_reads + n));
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n));
     const int ws = ctx->p.window_size;
-    if ((ctx->phred_mode == 1 || ctx->phred_mode == 2) && ws >= 16 && ws <= 256) {
-        const bool fused = ctx->phred_mode == 1;            // 1: k_phred_score (one pass); 2: k_phred_sum + k_phred_win
+    if (ctx->phred_mode != 0 && ws >= 16 && ws <= 256) {
         // default: one warp per read, both chains by exact grid arithmetic (k_phred_sum, k_phred_win)
         FL_CUDA(ctx, ctx->sc_order.reserve(n, 0, st));
         FL_TRY(fl_order_by_length(ctx, b.len, n, ctx->sc_order.p));
@@ -1169,9 +915,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
         a.w_mean = ctx->w_mean.p + wb; a.w_window = ctx->w_window.p + wb; a.w_passed = ctx->w_passed.p + wb;
         a.read_base = rb; a.row_base = wb;
         a.order = ctx->sc_order.p;
-        // k_phred_first sums up to here: the first window for the fused kernel (which starts at base ws, any
-        // alignment), the next 16-byte boundary for k_phred_sum (16-byte loads)
-        a.head_len = fused ? ws : (ws + 15) & ~15;
+        a.head_len = (ws + 15) & ~15;                     // k_phred_first sums up to here; k_phred_sum takes over (16-byte loads)
         FL_CUDA(ctx, ctx->sc_f64.reserve(3 * n + 8, 0, st));
         a.it_a = ctx->sc_f64.p; a.it_b = ctx->sc_f64.p + n; a.it_c = ctx->sc_f64.p + 2 * n;
         FL_CUDA(ctx, ctx->sc_u32a.reserve(n + 2, 0, st));
@@ -1184,9 +928,6 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_win<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_score<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_score<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-            FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_score<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_first, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             FL_CUDA(ctx, cudaFuncSetAttribute(k_phred_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, PH_SMEM));
             ctx->phred_attr_set = true;
@@ -1198,7 +939,7 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
             ctx->launches++;
         }
         unsigned blocks = fl_blocks(n * 32, PT_THREADS);
-        const int occ = ctx->phred_occupancy >= 1 && ctx->phred_occupancy <= 6 ? ctx->phred_occupancy : (fused ? 3 : 4);
+        const int occ = ctx->phred_occupancy >= 1 && ctx->phred_occupancy <= 6 ? ctx->phred_occupancy : 4;
         const unsigned cap = (unsigned)ctx->sm_count * (unsigned)occ;
         if (blocks > cap) blocks = cap;
         {
@@ -1208,18 +949,15 @@ int fl_score_phred(fl_ctx *ctx, const BatchView &b) {
             ti.any = ctx->tie_binades;
             ti.many = ctx->tie_many;
             memcpy(ti.ch, ctx->tie_char, 64);
-            if (fused) {
-                if (ws <= 64) k_phred_score<2><<<blocks, PT_THREADS, PF_SMEM, st>>>(a, ti);
-                else if (ws <= 128) k_phred_score<4><<<blocks, PT_THREADS, PF_SMEM, st>>>(a, ti);
-                else k_phred_score<8><<<blocks, PT_THREADS, PF_SMEM, st>>>(a, ti);
-                ctx->launches += 1;
-            } else {
-                k_phred_sum<<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ti);
-                if (ws <= 64) k_phred_win<2><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
-                else if (ws <= 128) k_phred_win<4><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
-                else k_phred_win<8><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
-                ctx->launches += 2;
-            }
+            // (One fused pass -- a 16-byte {q, a} gather per base feeding both chains, the step one window long -- was
+            // built and measured: 14 % MORE instructions, because the sum's bookkeeping then runs once per 250 bases
+            // instead of once per 512, and 80 registers / 24 warps per SM: 31.7 ms against 23.8. Evidence:
+            // profiles/r02_ncu_c2_phred_score_fused_scale0.25.json; the code is gone.)
+            k_phred_sum<<<blocks, PT_THREADS, PT_SMEM, st>>>(a, ti);
+            if (ws <= 64) k_phred_win<2><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
+            else if (ws <= 128) k_phred_win<4><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
+            else k_phred_win<8><<<blocks, PT_THREADS, PT_SMEM, st>>>(a);
+            ctx->launches += 2;
         }
         k_phred_fallback<<<ctx->sm_count, PH_THREADS, PH_SMEM, st>>>(a);   // reads the window kernel rejected (normally none)
         ctx->launches++;

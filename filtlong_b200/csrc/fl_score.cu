@@ -293,9 +293,11 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
                 a.item_len[a.n + rs_row + idx] = e - s;
             }
         };
+        uint32_t x_next = (int)lane < n_words ? __ldg(m + lane) : 0u;      // one step ahead: the loop body is a dependent chain
         for (int wb = 0; wb < n_words; wb += 32) {
             const int wi = wb + (int)lane;
-            const uint32_t x = wi < n_words ? __ldg(m + wi) : 0u;
+            const uint32_t x = x_next;
+            x_next = wi + 32 < n_words ? __ldg(m + wi + 32) : 0u;
             const unsigned nz = __ballot_sync(0xffffffffu, x != 0u);
             const int tzc = x ? __clz(x) : 32, lzc = x ? __ffs(x) - 1 : 32;
             // common case: every word of the step has a hit, nothing open from before can reach --split, and this is
@@ -529,12 +531,14 @@ struct WinArgs {
     unsigned long long *work;               // shared item counter
 };
 
-// bits [pos, pos + 32) of a mask whose last valid word is m[last_word]
-__device__ __forceinline__ uint32_t kw_bits(const uint32_t *__restrict__ m, long long pos, int last_word) {
+// the two mask words that hold bits [pos, pos + 32) (last valid word: m[last_word]); kw_bits = their funnel shift
+__device__ __forceinline__ uint2 kw_raw(const uint32_t *__restrict__ m, long long pos, int last_word) {
     const int wi = (int)(pos >> 5);
-    const uint32_t lo = __ldg(m + (wi <= last_word ? wi : last_word));
-    const uint32_t hi = __ldg(m + (wi + 1 <= last_word ? wi + 1 : last_word));
-    return __funnelshift_r(lo, hi, (unsigned)pos & 31u);
+    return make_uint2(__ldg(m + (wi <= last_word ? wi : last_word)), __ldg(m + (wi + 1 <= last_word ? wi + 1 : last_word)));
+}
+__device__ __forceinline__ uint32_t kw_bits(const uint32_t *__restrict__ m, long long pos, int last_word) {
+    const uint2 r = kw_raw(m, pos, last_word);
+    return __funnelshift_r(r.x, r.y, (unsigned)pos & 31u);
 }
 
 // popcount of bits [S, S + n) of the mask, by the whole warp
@@ -548,7 +552,7 @@ __device__ __forceinline__ int kw_popcount(const uint32_t *__restrict__ m, int S
     return __reduce_add_sync(0xffffffffu, cnt);
 }
 
-__global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
+__global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
     // nibble table: 4 steps with pure-plus bits p and pure-minus bits q (p & q == 0) ->
     // (delta + 4) | (lowest after-step partial sum + 4) << 4 | (highest + 4) << 8
     __shared__ unsigned short lut[256];
@@ -599,6 +603,14 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
             mean = 100.0 * (double)hits / (double)len;             // read.cpp:208-213 (0/0 = NaN for an empty read, as there)
             window = mean;
         } else {
+            // the first iteration's mask words are requested before the first window is counted (independent loads)
+            const int T = len - ws;                                // steps: base S + ws + t enters, base S + t leaves
+            const unsigned sh_in = (unsigned)(S + ws) & 31u, sh_out = (unsigned)S & 31u;     // (t0 and 32 * lane are multiples of 32)
+            uint2 raw_in = make_uint2(0u, 0u), raw_out = make_uint2(0u, 0u);
+            if (32 * (int)lane < T) {
+                raw_in = kw_raw(m, (long long)S + ws + 32 * (int)lane, last_word);
+                raw_out = kw_raw(m, (long long)S + 32 * (int)lane, last_word);
+            }
             int c = kw_popcount(m, S, ws, last_word, lane);        // read.cpp:220-222: the first window's sum is an exact integer
             const int c0 = c;
             int hits = 0;                                          // ones entering the window, per lane
@@ -606,19 +618,24 @@ __global__ void __launch_bounds__(256) k_kmer_window(WinArgs a) {
             KwAnchor an;
             kw_set_anchor(an, k, best, c);
             int cmin = c, trec = c;                                // lowest / highest after-step count of the current epoch
-            const int T = len - ws;                                // steps: base S + ws + t enters, base S + t leaves
+            // inside the loop the NEXT iteration's words are requested before this iteration's (dependent) arithmetic
+            // starts: one memory latency per 1024 steps would otherwise be all a warp does
             for (int t0 = 0; t0 < T; t0 += 1024) {
                 const int tl = t0 + 32 * (int)lane;
                 const int nv = T - tl;
                 uint32_t in = 0, out = 0;
                 if (nv > 0) {
-                    in = kw_bits(m, (long long)S + ws + tl, last_word);
-                    out = kw_bits(m, (long long)S + tl, last_word);
+                    in = __funnelshift_r(raw_in.x, raw_in.y, sh_in);
+                    out = __funnelshift_r(raw_out.x, raw_out.y, sh_out);
                     if (nv < 32) {
                         const uint32_t vm = (1u << nv) - 1u;
                         in &= vm;
                         out &= vm;
                     }
+                }
+                if (tl + 1024 < T) {
+                    raw_in = kw_raw(m, (long long)S + ws + tl + 1024, last_word);
+                    raw_out = kw_raw(m, (long long)S + tl + 1024, last_word);
                 }
                 hits += __popc(in);
                 const uint32_t pin = in & ~out, pout = out & ~in, both = in & out;
