@@ -572,12 +572,19 @@ __global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
     const KwConsts &k = a.k;
     const int ws = a.p.window_size;
     const double wsd = (double)ws;
+    // items come from a shared counter (longest first); a warp holds its NEXT item's index one row ahead, so that the
+    // dependent loads atomicAdd -> order[it] -> descriptors are not all paid at the start of every row
+    unsigned long long it_next = 0;
+    if (lane == 0) it_next = atomicAdd(a.work, 1ull);
+    it_next = __shfl_sync(0xffffffffu, it_next, 0);
+    uint32_t idx_next = it_next < a.n_items ? __ldg(a.order + it_next) : 0u;
     for (;;) {
-        unsigned long long it = 0;
-        if (lane == 0) it = atomicAdd(a.work, 1ull);
-        it = __shfl_sync(0xffffffffu, it, 0);
+        const unsigned long long it = it_next;
         if (it >= a.n_items) break;
-        const uint32_t idx = a.order[it];
+        const uint32_t idx = idx_next;
+        if (lane == 0) it_next = atomicAdd(a.work, 1ull);
+        it_next = __shfl_sync(0xffffffffu, it_next, 0);
+        idx_next = it_next < a.n_items ? __ldg(a.order + it_next) : 0u;
         uint32_t r;
         int S, E;
         long long row = -1;                                        // batch-local row this item writes (if any)

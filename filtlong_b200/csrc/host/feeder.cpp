@@ -10,6 +10,7 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <iostream>
@@ -450,46 +451,112 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     // ---- pass 2 ----
     std::cerr << "Outputting passed long reads\n";
     fflush(stdout);
-    Writer w;
     const char lead = format == FL_TEXT_FASTA ? '>' : '@';
-    static const char plus_nl[] = "+\n", nl[] = "\n", sp[] = " ";
-    for (auto &s : shards) {
+    // one output record; Sink is a Writer (iovecs into the mapping) or a Sizer / Copier (below)
+    auto emit_read = [&](auto &sink, const Shard &s, size_t i) {
+        static const char plus_nl[] = "+\n", nl[] = "\n", sp[] = " ";
         const Records &R = s.rec;
-        for (size_t i = 0; i < R.n; ++i) {
-            const size_t rs = (size_t)s.row_start[i];
-            const int nc = s.n_child[i];
-            if (nc == 0) {
-                if (!s.row_pfinal[rs]) continue;
-                // header line, sequence, '+', quality are contiguous in the file except for the '+' line's text: two slices
-                w.put(f.base + R.name_off[i] - 1, 1 + (size_t)R.name_len[i]);                        // '@' / '>' + name
-                if (R.comment_len[i]) { w.put(sp, 1); w.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
-                w.put(nl, 1);
-                w.put(f.base + R.seq_off[i], (size_t)R.len[i]);
-                w.put(nl, 1);
-                if (format == FL_TEXT_FASTQ) { w.put(plus_nl, 2); w.put(f.base + R.qual_off[i], (size_t)R.len[i]); w.put(nl, 1); }
-            } else {
-                for (int c = 0; c < nc; ++c) {
-                    const size_t row = rs + (size_t)c;
-                    if (!s.row_pfinal[row]) continue;
-                    const int start = s.row_s[row], length = s.row_e[row] - s.row_s[row];
-                    if (length <= 0) continue;
-                    std::string nm(1, lead);
-                    nm.append(f.base + R.name_off[i], R.name_len[i]);
-                    nm += "_" + std::to_string(start + 1) + "-" + std::to_string(s.row_e[row]);      // read.cpp:135-136
-                    w.put_owned(std::move(nm));
-                    if (R.comment_len[i]) { w.put(sp, 1); w.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
-                    w.put(nl, 1);
-                    w.put(f.base + R.seq_off[i] + start, (size_t)length);
-                    w.put(nl, 1);
-                    if (format == FL_TEXT_FASTQ) { w.put(plus_nl, 2); w.put(f.base + R.qual_off[i] + start, (size_t)length); w.put(nl, 1); }
-                }
-            }
+        const size_t rs = (size_t)s.row_start[i];
+        const int nc = s.n_child[i];
+        if (nc == 0) {
+            if (!s.row_pfinal[rs]) return;
+            sink.put(f.base + R.name_off[i] - 1, 1 + (size_t)R.name_len[i]);                        // '@' / '>' + name
+            if (R.comment_len[i]) { sink.put(sp, 1); sink.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
+            sink.put(nl, 1);
+            sink.put(f.base + R.seq_off[i], (size_t)R.len[i]);
+            sink.put(nl, 1);
+            if (format == FL_TEXT_FASTQ) { sink.put(plus_nl, 2); sink.put(f.base + R.qual_off[i], (size_t)R.len[i]); sink.put(nl, 1); }
+            return;
         }
+        for (int c = 0; c < nc; ++c) {
+            const size_t row = rs + (size_t)c;
+            if (!s.row_pfinal[row]) continue;
+            const int start = s.row_s[row], length = s.row_e[row] - s.row_s[row];
+            if (length <= 0) continue;
+            std::string nm(1, lead);
+            nm.append(f.base + R.name_off[i], R.name_len[i]);
+            nm += "_" + std::to_string(start + 1) + "-" + std::to_string(s.row_e[row]);              // read.cpp:135-136
+            sink.put_owned(std::move(nm));
+            if (R.comment_len[i]) { sink.put(sp, 1); sink.put(f.base + R.name_off[i] + R.name_len[i] + 1, R.comment_len[i]); }
+            sink.put(nl, 1);
+            sink.put(f.base + R.seq_off[i] + start, (size_t)length);
+            sink.put(nl, 1);
+            if (format == FL_TEXT_FASTQ) { sink.put(plus_nl, 2); sink.put(f.base + R.qual_off[i] + start, (size_t)length); sink.put(nl, 1); }
+        }
+    };
+    bool out_failed = false;
+    struct stat ost;
+    const int oflags = fcntl(STDOUT_FILENO, F_GETFL);
+    const bool to_file = fstat(STDOUT_FILENO, &ost) == 0 && S_ISREG(ost.st_mode) && oflags >= 0 && !(oflags & O_APPEND) && !getenv("FL_SERIAL_OUTPUT");
+    if (to_file) {
+        // stdout is a regular file: contiguous groups of reads are sized, then written with pwrite() by a few threads
+        struct Sizer {
+            uint64_t n = 0;
+            void put(const void *, size_t k) { n += k; }
+            void put_owned(std::string s) { n += s.size(); }
+        };
+        struct Copier {
+            int fd; uint64_t pos; std::string buf; bool failed = false;
+            void flush() {
+                size_t done = 0;
+                while (done < buf.size() && !failed) {
+                    const ssize_t w = pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(pos + done));
+                    if (w < 0) { failed = true; break; }
+                    done += (size_t)w;
+                }
+                pos += buf.size();
+                buf.clear();
+            }
+            void put(const void *p, size_t k) { buf.append((const char *)p, k); if (buf.size() >= (8u << 20)) flush(); }
+            void put_owned(std::string s) { put(s.data(), s.size()); }
+        };
+        struct Group { size_t shard, lo, hi; uint64_t bytes = 0, at = 0; };
+        std::vector<Group> groups;
+        const size_t per = (size_t)(n_reads / 32) + 1;
+        for (size_t si = 0; si < shards.size(); ++si)
+            for (size_t lo = 0; lo < shards[si].rec.n; lo += per) groups.push_back(Group{si, lo, std::min(lo + per, shards[si].rec.n), 0, 0});
+        const off_t base_pos = lseek(STDOUT_FILENO, 0, SEEK_CUR);
+        std::atomic<size_t> next(0);
+        auto work = [&](bool write_pass) {
+            std::vector<std::thread> ts;
+            next.store(0);
+            std::atomic<bool> bad(false);
+            const unsigned nt = std::min<size_t>(8, groups.size());
+            for (unsigned t = 0; t < nt; ++t)
+                ts.emplace_back([&] {
+                    for (size_t g = next.fetch_add(1); g < groups.size(); g = next.fetch_add(1)) {
+                        Group &G = groups[g];
+                        if (!write_pass) {
+                            Sizer z;
+                            for (size_t i = G.lo; i < G.hi; ++i) emit_read(z, shards[G.shard], i);
+                            G.bytes = z.n;
+                        } else {
+                            Copier c{STDOUT_FILENO, (uint64_t)base_pos + G.at, std::string()};
+                            c.buf.reserve((8u << 20) + (2u << 20));
+                            for (size_t i = G.lo; i < G.hi; ++i) emit_read(c, shards[G.shard], i);
+                            c.flush();
+                            if (c.failed) bad.store(true);
+                        }
+                    }
+                });
+            for (auto &t : ts) t.join();
+            return !bad.load();
+        };
+        work(false);
+        uint64_t total_out = 0;
+        for (auto &G : groups) { G.at = total_out; total_out += G.bytes; }
+        if (base_pos < 0 || !work(true)) out_failed = true;
+        else if (lseek(STDOUT_FILENO, base_pos + (off_t)total_out, SEEK_SET) < 0) out_failed = true;
+    } else {
+        Writer w;
+        for (auto &s : shards)
+            for (size_t i = 0; i < s.rec.n; ++i) emit_read(w, s, i);
+        w.flush();
+        out_failed = w.failed;
     }
-    w.flush();
     mark("pass 2 (slices of the mapped input)");
     std::cerr << "\n";
     cleanup();
-    res.exit_code = w.failed ? 1 : 0;
+    res.exit_code = out_failed ? 1 : 0;
     return res;
 }

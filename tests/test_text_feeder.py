@@ -163,6 +163,15 @@ def test_cli_device_parse_path_is_byte_identical_to_the_reference(case, last_new
     assert out_o == out_r
     rc_h, out_h, err_h = run([CLI] + args, {"FL_HOST_PARSER": "1"})
     assert rc_h == 0 and out_h == out_r
+    # stdout a regular file: groups of reads are sized and written with pwrite() by several threads
+    with open(tmp_path / "out.txt", "wb") as fh:
+        fh.write(b"HEAD\n")
+        fh.flush()
+        e = dict(os.environ, LC_ALL="C", FL_CHUNK_MB="1")
+        e.pop("LANG", None)
+        assert subprocess.run([CLI] + args, stdout=fh, stderr=subprocess.DEVNULL, env=e).returncode == 0
+        fh.write(b"TAIL\n")
+    assert (tmp_path / "out.txt").read_bytes() == b"HEAD\n" + out_r + b"TAIL\n"
     tail = lambda e: [l.split("\r")[-1] for l in e.splitlines() if l.strip() and "[timing]" not in l and "bp)" not in l]
     assert tail(err_o) == tail(err_r)
 

@@ -2,7 +2,7 @@
 # gpurun --gpus 2: the NCCL path behind the C ABI (tests), the sharded CLI, the full bench on 2 ranks
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_n2.txt 2>&1
-(timeout 900 python -m pytest tests/test_nccl_ranks.py "tests/test_text_feeder.py::test_cli_sharded_over_gpus_prints_what_one_gpu_prints" -m gpu -q 2>&1 | tail -40) > gpurun_out/pytest_n2.log 2>&1
+(timeout 1200 python -m pytest tests/test_nccl_ranks.py "tests/test_text_feeder.py::test_cli_sharded_over_gpus_prints_what_one_gpu_prints" tests/test_gpu_parity.py tests/test_golden.py -m gpu -q 2>&1 | tail -40) > gpurun_out/pytest_n2.log 2>&1
 tail -6 gpurun_out/pytest_n2.log
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
 tail -4 gpurun_out/bench_n2.err

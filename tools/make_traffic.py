@@ -49,7 +49,7 @@ def main():
         a[0] += 1; a[1] += e.get("ms", 0.0); a[2] += e.get("bytes", 0.0)
     table = [{"kernel": k, "launches": n, "total_ms": round(ms, 3), "dram_bytes_per_launch": int(b / n)} for k, (n, ms, b) in
              sorted(agg.items(), key=lambda x: -x[1][1])]
-    sel = [t for t in table if any(t["kernel"].split("<")[0].endswith(k) for k in kernels)]
+    sel = [t for t in table if any(k in t["kernel"] for k in kernels)]
     # bytes of one scoring pass = sum over the named kernels of their per-launch bytes (each runs once per step)
     total = sum(t["dram_bytes_per_launch"] for t in sel)
     for tag in tags:
