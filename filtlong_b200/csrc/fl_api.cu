@@ -90,6 +90,8 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->comm) fl_comm_destroy(c);
+    if (c->d_comm) cudaFree(c->d_comm);
     drain_timers(c);
     if (c->d_bitmap) cudaFree(c->d_bitmap);
     if (c->d_filter) cudaFree(c->d_filter);

@@ -198,7 +198,10 @@ def test_cli_sharded_over_gpus_prints_what_one_gpu_prints(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
     genome, reads = make_reads(21, n=600)
-    reads = reads + [(n + b"_again", s, q) for n, s, q in reads[:50]]          # exact score ties across shards
+    def again(n):
+        name, sep, comment = n.partition(b" ")
+        return name + b"_again" + sep + comment
+    reads = reads + [(again(n), s, q) for n, s, q in reads[:50]]                # exact score ties across shards
     fq = tmp_path / "reads.fastq"
     fq.write_bytes(fastq_text(reads))
     fa = util.write_fasta(tmp_path / "asm.fasta", [("c", genome)])
