@@ -25,6 +25,30 @@
 
 namespace {
 
+// The records go to the descriptor stdout had at start-up. With more than one GPU, fd 1 itself is pointed at stderr while the
+// run lasts: NCCL (NCCL_DEBUG=VERSION/WARN/INFO) and other libraries print to "stdout", which here is the data stream.
+int g_out_fd = 1;
+struct StdoutGuard {
+    bool on = false;
+    void engage() {
+        if (on) return;
+        fflush(stdout);
+        const int d = dup(1);
+        if (d < 0) return;
+        if (dup2(2, 1) < 0) { close(d); return; }
+        g_out_fd = d;
+        on = true;
+    }
+    void release() {                 // the host parser (std::cout) takes over: give it the real stdout back
+        if (!on) return;
+        fflush(stdout);
+        dup2(g_out_fd, 1);
+        close(g_out_fd);
+        g_out_fd = 1;
+        on = false;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // the input, mapped
 // ---------------------------------------------------------------------------------------------
@@ -316,7 +340,7 @@ struct Writer {
     void flush() {
         int done = 0;
         while (done < nv && !failed) {
-            ssize_t w = writev(STDOUT_FILENO, v + done, nv - done);
+            ssize_t w = writev(g_out_fd, v + done, nv - done);
             if (w < 0) { failed = true; break; }
             while (done < nv && (size_t)w >= v[done].iov_len) { w -= (ssize_t)v[done].iov_len; ++done; }
             if (done < nv && w > 0) { v[done].iov_base = (char *)v[done].iov_base + w; v[done].iov_len -= (size_t)w; }
@@ -361,6 +385,8 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
 
     const fl_params params = params_from_arguments(args);
     unsigned char comm_id[FL_COMM_ID_BYTES] = {0};
+    StdoutGuard guard;
+    if (nranks > 1) guard.engage();
     if (nranks > 1 && fl_comm_unique_id(comm_id) != FL_OK) throw std::runtime_error("NCCL is not available: cannot shard across GPUs");
     // contiguous chunk ranges, balanced by bytes (file order is kept: shard r holds the records before shard r + 1's)
     std::vector<Shard> shards((size_t)nranks);
@@ -398,6 +424,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     if (abort_all.load()) {                                             // not the simple layout after all: start over on the host
         if (ctx0) fl_reads_reset(ctx0);
         cleanup();
+        guard.release();
         return res;
     }
     mark("pass 1 (device parse + score)");
@@ -486,8 +513,8 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     };
     bool out_failed = false;
     struct stat ost;
-    const int oflags = fcntl(STDOUT_FILENO, F_GETFL);
-    const bool to_file = fstat(STDOUT_FILENO, &ost) == 0 && S_ISREG(ost.st_mode) && oflags >= 0 && !(oflags & O_APPEND) && !getenv("FL_SERIAL_OUTPUT");
+    const int oflags = fcntl(g_out_fd, F_GETFL);
+    const bool to_file = fstat(g_out_fd, &ost) == 0 && S_ISREG(ost.st_mode) && oflags >= 0 && !(oflags & O_APPEND) && !getenv("FL_SERIAL_OUTPUT");
     if (to_file) {
         // stdout is a regular file: contiguous groups of reads are sized, then written with pwrite() by a few threads
         struct Sizer {
@@ -515,7 +542,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
         const size_t per = (size_t)(n_reads / 32) + 1;
         for (size_t si = 0; si < shards.size(); ++si)
             for (size_t lo = 0; lo < shards[si].rec.n; lo += per) groups.push_back(Group{si, lo, std::min(lo + per, shards[si].rec.n), 0, 0});
-        const off_t base_pos = lseek(STDOUT_FILENO, 0, SEEK_CUR);
+        const off_t base_pos = lseek(g_out_fd, 0, SEEK_CUR);
         std::atomic<size_t> next(0);
         auto work = [&](bool write_pass) {
             std::vector<std::thread> ts;
@@ -531,7 +558,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
                             for (size_t i = G.lo; i < G.hi; ++i) emit_read(z, shards[G.shard], i);
                             G.bytes = z.n;
                         } else {
-                            Copier c{STDOUT_FILENO, (uint64_t)base_pos + G.at, std::string()};
+                            Copier c{g_out_fd, (uint64_t)base_pos + G.at, std::string()};
                             c.buf.reserve((8u << 20) + (2u << 20));
                             for (size_t i = G.lo; i < G.hi; ++i) emit_read(c, shards[G.shard], i);
                             c.flush();
@@ -546,7 +573,7 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
         uint64_t total_out = 0;
         for (auto &G : groups) { G.at = total_out; total_out += G.bytes; }
         if (base_pos < 0 || !work(true)) out_failed = true;
-        else if (lseek(STDOUT_FILENO, base_pos + (off_t)total_out, SEEK_SET) < 0) out_failed = true;
+        else if (lseek(g_out_fd, base_pos + (off_t)total_out, SEEK_SET) < 0) out_failed = true;
     } else {
         Writer w;
         for (auto &s : shards)

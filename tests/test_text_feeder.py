@@ -207,6 +207,6 @@ def test_cli_sharded_over_gpus_prints_what_one_gpu_prints(tmp_path):
     fa = util.write_fasta(tmp_path / "asm.fasta", [("c", genome)])
     for case in (["-p", "60", str(fq)], ["-a", fa, "-p", "70", "--trim", "--split", "100", str(fq)]):
         rc1, out1, err1 = run([CLI] + case, {"FL_CHUNK_MB": "1"})
-        rc2, out2, err2 = run([CLI, "--gpus", "2"] + case, {"FL_CHUNK_MB": "1"})
+        rc2, out2, err2 = run([CLI, "--gpus", "2"] + case, {"FL_CHUNK_MB": "1", "NCCL_DEBUG": "VERSION"})   # NCCL chats on "stdout"
         assert rc1 == rc2 == 0, err2[-2000:]
         assert out1 == out2
