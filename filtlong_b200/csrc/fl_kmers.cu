@@ -194,10 +194,27 @@ __global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            uint32_t word;
-            unsigned long long fb;
-            fl_filter_slot((uint32_t)(w << 5) | (uint32_t)b, log2_words, kind, word, fb);
-            if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
+            const uint32_t kmer = (uint32_t)(w << 5) | (uint32_t)b;
+            if (kind & 4) {                                  // group of 4: once per alignment, like the anchored table
+#pragma unroll
+                for (unsigned r = 0; r < 4; ++r) {
+                    const uint32_t word = fl_filter_word_group4(kmer, r, log2_words);
+                    const unsigned long long fb = fl_filter_bits_role(kmer, r);
+                    if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
+                }
+            } else if (kind & 8) {                           // pair: as the earlier and as the later neighbour
+#pragma unroll
+                for (unsigned role = 0; role < 2; ++role) {
+                    const uint32_t word = fl_filter_word_pair(kmer, role, log2_words);
+                    const unsigned long long fb = fl_filter_bits_role(kmer, role);
+                    if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
+                }
+            } else {
+                uint32_t word;
+                unsigned long long fb;
+                fl_filter_slot(kmer, log2_words, kind, word, fb);
+                if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
+            }
         }
     }
 }

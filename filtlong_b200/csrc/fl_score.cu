@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
                 uint32_t go = 0xFFFFu;                // which of the 16 k-mers still need the exact bitmap
-                if (FILT) {
+                if (FILT == 1) {
                     // 16 independent loads from the 32 MiB pre-filter (kept in L2): most k-mers of a
                     // noisy read are absent and stop here, without touching HBM
                     unsigned long long f[16];
@@ -163,6 +163,38 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         go |= ((f[i] & fb) == fb ? 1u : 0u) << i;
                     }
                 }
+                if (FILT == 2) {
+                    // group-keyed pre-filter: the four 16-mers of a table group share ONE filter word (4 loads per half, not 16)
+                    unsigned long long f[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int p0 = half * 16 + 4 * g;
+                        const uint32_t word = fl_filter_word_group4(fl_kmer_at(w, p0 + 3), 0u, a.filter_log2_words);
+                        f[g] = p0 < nvalid ? __ldcg(a.filter + word) : 0ull;
+                    }
+                    go = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), 3u - (unsigned)(i & 3));
+                        go |= ((f[i >> 2] & fb) == fb ? 1u : 0u) << i;
+                    }
+                }
+                if (FILT == 3) {
+                    // pair-keyed pre-filter: two neighbouring 16-mers share a word (8 loads per half)
+                    unsigned long long f[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int p0 = half * 16 + 2 * q;
+                        const uint32_t word = fl_filter_word_pair(fl_kmer_at(w, p0), 0u, a.filter_log2_words);
+                        f[q] = p0 < nvalid ? __ldcg(a.filter + word) : 0ull;
+                    }
+                    go = 0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), (unsigned)(i & 1));
+                        go |= ((f[i >> 1] & fb) == fb ? 1u : 0u) << i;
+                    }
+                }
                 if (ANCH) {
                     // the four 16-mers starting at 4g .. 4g+3 of the lane's run (a multiple of 32, so of 4)
                     // share one 32-byte sector of the anchored table: ONE 256-bit load per group
@@ -173,10 +205,16 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         const uint32_t key = (fl_kmer_at(w, p0 + 3) >> 6) & 0x3FFFFFFu;   // bases p0+3 .. p0+15
                         const bool need = p0 < nvalid && ((go >> (4 * g)) & 0xFu);
                         if (need) {
-                            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                         : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                           "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                         : "l"(table + (size_t)key * 8u));
+                            if (MODE == 4)
+                                asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                             : "l"(table + (size_t)key * 8u));
+                            else
+                                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                             : "l"(table + (size_t)key * 8u));
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
@@ -843,8 +881,18 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
             // de-duplication (L1TEX 83 % -> 31 %, but 5x the false positives and the filter falls out of L2: 128 ms against
             // 94 ms), L2 eviction hints and the persisting-L2 window on either flavour (+4..8 ms).
             if (ctx->use_anchor) {
-                if (ctx->use_filter) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
-                else k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
+                const int filt = !ctx->use_filter ? 0 : ((ctx->filter_kind & 4) ? 2 : ((ctx->filter_kind & 8) ? 3 : 1));
+                if (ctx->probe_mode == 4) {
+                    if (filt == 0) k_probe_paint<4, 0, true><<<blocks, 256, 0, st>>>(pa);
+                    else if (filt == 1) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa);
+                    else if (filt == 2) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa);
+                    else k_probe_paint<4, 3, true><<<blocks, 256, 0, st>>>(pa);
+                } else {
+                    if (filt == 0) k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
+                    else if (filt == 1) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
+                    else if (filt == 2) k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa);
+                    else k_probe_paint<2, 3, true><<<blocks, 256, 0, st>>>(pa);
+                }
             } else if (ctx->use_filter) {                        // plain bitmap (FL_ANCHOR=0: cross-checks and profiling)
                 k_probe_paint<2, 1, false><<<blocks, 256, 0, st>>>(pa);
             } else {
