@@ -63,6 +63,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     c->stream = c->own_stream;
     // tuning knobs for profiling runs (defaults are the measured best, see profiles/ and DESIGN.md section 7)
     if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
+    if (const char *m = getenv("FL_PROBE_WIDE")) c->probe_wide = atoi(m);
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
     if (const char *f = getenv("FL_ANCHOR")) c->anchor_enabled = atoi(f);
     if (const char *f = getenv("FL_PHRED_MODE")) c->phred_mode = atoi(f);
@@ -103,6 +104,7 @@ extern "C" void fl_ctx_destroy(fl_ctx *c) {
     if (c->d_buckets) cudaFree(c->d_buckets);
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->h_scalars) cudaFreeHost(c->h_scalars);
+    if (c->ev_rows) cudaEventDestroy(c->ev_rows);
     fl_norm_select_free(c);
     for (int i = 0; i < 2; ++i) if (c->stg[i].consumed) cudaEventDestroy(c->stg[i].consumed);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
@@ -393,9 +395,9 @@ __global__ void k_sum_len(const int32_t *len, uint32_t n, unsigned long long *ou
 #define FL_SCALAR_TOTAL_BASES 16   // slot in d_scalars accumulating the lengths of device batches
 
 extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
-    FL_ENTER(c);
+    FL_ENTER_NOFLUSH(c);
     FL_TRY(check_batch(c, h));
-    if (h->n == 0) return FL_OK;
+    if (h->n == 0) return fl_score_complete(c);
     if (c->kmers_count_stale || c->multi_pending) FL_TRY(fl_kmers_recount(c));
     const bool kmer_mode = c->n_kmers > 0;
     BatchView v{};
@@ -406,11 +408,17 @@ extern "C" int fl_reads_push(fl_ctx *c, const fl_batch *h) {
     FL_TRY(staging_acquire(c, slot));
     FL_TRY(stage_host_batch(c, h, &v, kmer_mode, !kmer_mode, false, slot, c->copy_stream));
     FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+    // With --trim / --split the previous batch still owes its second half, which starts with a host round trip (its row
+    // count). Paying it HERE, with this batch's copy already under way, keeps the copy engine busy during that batch's probe.
+    FL_TRY(fl_score_complete(c));
     FL_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
     FL_TRY(stage_pack(c, &v, false, slot));
-    FL_TRY(fl_score_view(c, v));
-    FL_CUDA(c, cudaEventRecord(c->stg[slot].consumed, c->stream));
-    c->stg[slot].in_use = true;
+    FL_TRY(fl_score_view(c, v, /*defer=*/true));
+    if (c->kmer_pending) c->kmer_pending_slot = slot;            // fl_score_complete releases the slot
+    else {
+        FL_CUDA(c, cudaEventRecord(c->stg[slot].consumed, c->stream));
+        c->stg[slot].in_use = true;
+    }
     for (uint32_t i = 0; i < h->n; ++i) c->total_bases += h->len[i];     // main.cpp:89
     FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the caller may reuse its host buffers now
     return FL_OK;

@@ -131,15 +131,18 @@ __device__ __forceinline__ void fl_filter_slot(uint32_t kmer, unsigned log2_word
     const uint32_t h2 = (kmer ^ (kmer >> 15)) * 0x85EBCA6Bu;
     word = h1 >> (32 - log2_words);
     bits = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
+    if (kind & 16) bits |= (1ull << ((h2 >> 14) & 63u)) | (1ull << ((h2 >> 8) & 63u));   // four bits per member
 }
 
 // Group-keyed flavours of the pre-filter (FL_FILTER_KIND bit 2 / bit 3): the WORD is chosen by what a run of consecutive
 // 16-mers of a read has in common, so ONE load answers for the whole run, and each 16-mer keeps its own two bits.
 //   group of 4 (the anchored table's group): the 13-base key of fl_anchor_slot(kmer, r); a member is inserted four times (r = 0..3)
 //   pair: the 15 bases two neighbours share; role 0 = the earlier one (its low 30 bits), role 1 = the later one (its high 30 bits)
-__host__ __device__ __forceinline__ unsigned long long fl_filter_bits_role(uint32_t kmer, unsigned role) {
+__host__ __device__ __forceinline__ unsigned long long fl_filter_bits_role(uint32_t kmer, unsigned role, int kind) {
     const uint32_t h2 = ((kmer ^ (kmer >> 15)) + role * 0x632BE5ABu) * 0x85EBCA6Bu;
-    return (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
+    unsigned long long bits = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));
+    if (kind & 16) bits |= (1ull << ((h2 >> 14) & 63u)) | (1ull << ((h2 >> 8) & 63u));
+    return bits;
 }
 __host__ __device__ __forceinline__ uint32_t fl_filter_word_group4(uint32_t kmer, unsigned r, unsigned log2_words) {
     const uint32_t key = (kmer >> (6u - 2u * r)) & 0x3FFFFFFu;

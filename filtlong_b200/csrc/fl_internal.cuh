@@ -32,10 +32,20 @@
     } while (0)
 
 // every public entry point runs on its context's device (one process may hold one context per GPU)
-#define FL_ENTER(c)                                   \
+#define FL_ENTER_NOFLUSH(c)                           \
     do {                                              \
         if (!(c)) return FL_EINVAL;                   \
         FL_CUDA((c), cudaSetDevice((c)->device));     \
+    } while (0)
+
+// every entry point but fl_reads_push first finishes a batch whose second half was deferred (fl_score_complete)
+#define FL_ENTER(c)                                             \
+    do {                                                        \
+        FL_ENTER_NOFLUSH(c);                                    \
+        if ((c)->kmer_pending) {                                \
+            int rc_pending__ = fl_score_complete(c);            \
+            if (rc_pending__ != FL_OK) return rc_pending__;     \
+        }                                                       \
     } while (0)
 
 #define FL_TRY(expr)                \
@@ -102,6 +112,8 @@ struct SelectState {
     unsigned long long tie_base;     // bases the tie class may still take: target - cum_before
 };
 
+#define FL_HSCALAR_ROWS 40
+
 struct fl_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -109,6 +121,7 @@ struct fl_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
+    int probe_wide = 0;        // dense sets: 8 table sectors in flight per thread (FL_PROBE_WIDE)
     int probe_mode = 2;        // load flavour of the bitmap probe (fl_score.cu; 2 = ld.global.nc.L1::no_allocate, measured best); FL_PROBE_MODE overrides
 
     // ---- Kmers ----
@@ -170,6 +183,11 @@ struct fl_ctx {
     uint32_t *d_buckets = nullptr;         // 256 bucket counters + 256 cursors (fl_order_by_length)
     unsigned long long *d_scalars = nullptr;   // small device scalars (counts, cursors)
     unsigned long long *h_scalars = nullptr;   // pinned mirror
+    // second half of a k-mer batch with --trim / --split, deferred by fl_reads_push (fl_score.cu: score_kmer_back)
+    bool kmer_pending = false;
+    BatchView kmer_pending_view{};
+    int kmer_pending_slot = -1;             // staging slot to release once the deferred kernels are queued
+    cudaEvent_t ev_rows = nullptr;          // the batch's row count has reached h_scalars[FL_HSCALAR_ROWS]
 
     // ---- results: one entry per INPUT READ ----
     uint64_t n_reads = 0;
@@ -250,7 +268,10 @@ int fl_kmers_add_view(fl_ctx *ctx, const BatchView &b, int multi);
 int fl_kmers_recount(fl_ctx *ctx);
 
 // ---- implemented in fl_score.cu ----
-int fl_score_view(fl_ctx *ctx, const BatchView &b);
+// defer = the caller will call fl_score_complete() later (fl_reads_push: after the NEXT batch's copy is under way), so
+// that the one host round trip of --trim / --split (how many rows did this batch make?) does not stall the copy pipeline
+int fl_score_view(fl_ctx *ctx, const BatchView &b, bool defer = false);
+int fl_score_complete(fl_ctx *ctx);
 int fl_reserve_reads(fl_ctx *ctx, size_t n_total);
 int fl_reserve_rows(fl_ctx *ctx, size_t n_total);
 

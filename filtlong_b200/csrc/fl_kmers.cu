@@ -199,14 +199,14 @@ __global__ void __launch_bounds__(256) k_filter_build(const uint32_t *__restrict
 #pragma unroll
                 for (unsigned r = 0; r < 4; ++r) {
                     const uint32_t word = fl_filter_word_group4(kmer, r, log2_words);
-                    const unsigned long long fb = fl_filter_bits_role(kmer, r);
+                    const unsigned long long fb = fl_filter_bits_role(kmer, r, kind);
                     if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
                 }
             } else if (kind & 8) {                           // pair: as the earlier and as the later neighbour
 #pragma unroll
                 for (unsigned role = 0; role < 2; ++role) {
                     const uint32_t word = fl_filter_word_pair(kmer, role, log2_words);
-                    const unsigned long long fb = fl_filter_bits_role(kmer, role);
+                    const unsigned long long fb = fl_filter_bits_role(kmer, role, kind);
                     if ((filter[word] & fb) != fb) atomicOr(filter + word, fb);
                 }
             } else {

@@ -47,6 +47,7 @@ struct ProbeArgs {
     unsigned filter_log2_words;
     int filter_kind;
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
+    uint32_t zero;                           // 0 (see WIDE)
 };
 
 // One 4-byte load from the 512 MiB membership bitmap per k-mer. The flavour of the load decides how
@@ -91,8 +92,10 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
     return __ldg(p);
 }
 
-template <int MODE, int FILT, bool ANCH>
-__global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
+// WIDE (dense sets, no pre-filter): all eight table sectors of a lane's 32 k-mers are requested before the first is looked
+// at (64 data registers, so 3 blocks per SM instead of 4, but 8 instead of ~4.5 sector requests in flight per thread)
+template <int MODE, int FILT, bool ANCH, bool WIDE = false>
+__global__ void __launch_bounds__(256, WIDE ? 3 : 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
     const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
@@ -135,6 +138,41 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             long long nv = (long long)L - (FL_K - 1) - (long long)lb;
             const int nvalid = nv <= 0 ? 0 : (nv >= 32 ? 32 : (int)nv);
             uint32_t h = 0;
+            if (WIDE) {
+                uint32_t sec[8][8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const uint32_t key = (fl_kmer_at(w, 4 * g + 3) >> 6) & 0x3FFFFFFu;
+                    if (4 * g < nvalid) {
+                        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                       "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                     : "l"(table + (size_t)key * 8u));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
+                    }
+                }
+                // ptxas schedules the look-ups between the requests unless they depend on all eight: z is zero (a.zero is),
+                // but only the host knows
+                uint32_t z = sec[0][0];
+#pragma unroll
+                for (int g = 1; g < 8; ++g) z |= sec[g][0];
+                z &= a.zero;
+                LaneWords wz;
+                wz.w0 = w.w0 ^ z; wz.w1 = w.w1 ^ z; wz.w2 = w.w2 ^ z;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int p = 4 * g + j;
+                        uint32_t word, bit;
+                        fl_anchor_slot(fl_kmer_at(wz, p), 3u - (unsigned)j, word, bit);
+                        const uint32_t v = (word & 1u) ? sec[g][2 * (3 - j) + 1] : sec[g][2 * (3 - j)];
+                        h |= (((v >> bit) & 1u) & (p < nvalid ? 1u : 0u)) << p;
+                    }
+                }
+            } else {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
@@ -175,7 +213,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     go = 0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), 3u - (unsigned)(i & 3));
+                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), 3u - (unsigned)(i & 3), a.filter_kind);
                         go |= ((f[i >> 2] & fb) == fb ? 1u : 0u) << i;
                     }
                 }
@@ -191,7 +229,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     go = 0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), (unsigned)(i & 1));
+                        const unsigned long long fb = fl_filter_bits_role(fl_kmer_at(w, half * 16 + i), (unsigned)(i & 1), a.filter_kind);
                         go |= ((f[i >> 1] & fb) == fb ? 1u : 0u) << i;
                     }
                 }
@@ -246,6 +284,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         h |= ((words[i] >> (k & 31)) & 1u) << p;
                     }
                 }
+            }
             }
             // paint: base covered if any of the 16 k-mers ending at or after it hit (read.cpp:53-54)
             uint32_t prev = __shfl_up_sync(0xffffffffu, h, 1);
@@ -840,7 +879,27 @@ static void kw_make_consts(int ws, KwConsts *k) {
     }
 }
 
-static int score_kmer(fl_ctx *ctx, const BatchView &b) {
+// k-mer mode, first half: probe + paint, then the counting pass of k_kmer_scan; with --trim / --split it ends by sending the
+// batch's row count to the host (ev_rows), which score_kmer_back waits for
+static ScanArgs scan_args_of(fl_ctx *ctx, const BatchView &b) {
+    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+    ScanArgs sa{};
+    sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.len = b.len; sa.n = b.n; sa.p = ctx->p;
+    sa.r_len = ctx->r_len.p + rb; sa.r_first = ctx->r_first.p + rb; sa.r_last = ctx->r_last.p + rb;
+    sa.r_nbad = ctx->r_nbad.p + rb; sa.r_nchild = ctx->r_nchild.p + rb;
+    sa.r_rowstart = ctx->r_rowstart.p + rb; sa.rows_per_read = ctx->sc_u64b.p;
+    sa.item_len = ctx->sc_items.p;
+    sa.read_base = rb; sa.row_base = wb;
+    return sa;
+}
+
+static unsigned scan_blocks_of(fl_ctx *ctx, size_t n) {
+    unsigned scan_blocks = fl_blocks(n * 32, 256);
+    if (scan_blocks > (unsigned)ctx->sm_count * 8) scan_blocks = (unsigned)ctx->sm_count * 8;
+    return scan_blocks;
+}
+
+static int score_kmer_front(fl_ctx *ctx, const BatchView &b) {
     if (!b.seq2b) { ctx->set_error("k-mer scoring needs seq2b"); return FL_EINVAL; }
     const size_t n = b.n;
     cudaStream_t st = ctx->stream;
@@ -887,6 +946,9 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
                     else if (filt == 1) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa);
                     else if (filt == 2) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa);
                     else k_probe_paint<4, 3, true><<<blocks, 256, 0, st>>>(pa);
+                } else if (filt == 0 && ctx->probe_wide) {
+                    const unsigned wide_blocks = blocks < (unsigned)ctx->sm_count * 3 ? blocks : (unsigned)ctx->sm_count * 3;
+                    k_probe_paint<2, 0, true, true><<<wide_blocks, 256, 0, st>>>(pa);
                 } else {
                     if (filt == 0) k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
                     else if (filt == 1) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
@@ -907,28 +969,33 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
         ctx->launches++;
         FL_CUDA(ctx, cudaGetLastError());
     }
-    // ---- B: first / last, bad ranges, children (k_kmer_scan), then mean + window quality per item (k_kmer_window) ----
-    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
-    const bool may_have_children = ctx->p.trim || ctx->p.split_set;
+    // ---- B, counting pass: first / last, bad ranges, how many children (k_kmer_scan) ----
+    const size_t rb = ctx->n_reads;
     FL_CUDA(ctx, ctx->sc_u64b.reserve(n + 1, 0, st));
     FL_CUDA(ctx, ctx->sc_items.reserve(n + 8, 0, st));
-    ScanArgs sa{};
-    sa.mask = ctx->sc_mask.p; sa.off = b.off; sa.len = b.len; sa.n = b.n; sa.p = ctx->p;
-    sa.r_len = ctx->r_len.p + rb; sa.r_first = ctx->r_first.p + rb; sa.r_last = ctx->r_last.p + rb;
-    sa.r_nbad = ctx->r_nbad.p + rb; sa.r_nchild = ctx->r_nchild.p + rb;
-    sa.r_rowstart = ctx->r_rowstart.p + rb; sa.rows_per_read = ctx->sc_u64b.p;
-    sa.item_len = ctx->sc_items.p;
-    sa.read_base = rb; sa.row_base = wb;
-    unsigned scan_blocks = fl_blocks(n * 32, 256);
-    if (scan_blocks > (unsigned)ctx->sm_count * 8) scan_blocks = (unsigned)ctx->sm_count * 8;
-    k_kmer_scan<false><<<scan_blocks, 256, 0, st>>>(sa);
+    const ScanArgs sa = scan_args_of(ctx, b);
+    k_kmer_scan<false><<<scan_blocks_of(ctx, n), 256, 0, st>>>(sa);
     ctx->launches++;
+    if (ctx->p.trim || ctx->p.split_set) {
+        FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64b.p, ctx->r_rowstart.p + rb, n, ctx->d_scalars));
+        FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars + FL_HSCALAR_ROWS, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (!ctx->ev_rows) FL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming));
+        FL_CUDA(ctx, cudaEventRecord(ctx->ev_rows, st));
+    }
+    FL_CUDA(ctx, cudaGetLastError());
+    return FL_OK;
+}
+
+// k-mer mode, second half: rows (children or the reads themselves), then mean + window quality per item (k_kmer_window)
+static int score_kmer_back(fl_ctx *ctx, const BatchView &b) {
+    const size_t n = b.n;
+    cudaStream_t st = ctx->stream;
+    const size_t rb = ctx->n_reads, wb = ctx->n_rows;
+    const bool may_have_children = ctx->p.trim || ctx->p.split_set;
     size_t n_rows_batch = n;
     if (may_have_children) {
-        FL_TRY(fl_exclusive_scan_u64(ctx, ctx->sc_u64b.p, ctx->r_rowstart.p + rb, n, ctx->d_scalars));
-        FL_CUDA(ctx, cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        FL_CUDA(ctx, cudaStreamSynchronize(st));
-        n_rows_batch = (size_t)ctx->h_scalars[0];
+        FL_CUDA(ctx, cudaEventSynchronize(ctx->ev_rows));            // the one host round trip of the path
+        n_rows_batch = (size_t)ctx->h_scalars[FL_HSCALAR_ROWS];
     }
     FL_TRY(fl_reserve_rows(ctx, ctx->n_rows + n_rows_batch));
     size_t n_items = n;
@@ -939,9 +1006,9 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     } else {
         n_items = n + n_rows_batch;
         FL_CUDA(ctx, ctx->sc_items.reserve(n_items + 8, n, st));
-        sa.item_len = ctx->sc_items.p;
+        ScanArgs sa = scan_args_of(ctx, b);
         sa.w_parent = ctx->w_parent.p + wb; sa.w_start = ctx->w_start.p + wb; sa.w_end = ctx->w_end.p + wb;
-        k_kmer_scan<true><<<scan_blocks, 256, 0, st>>>(sa);
+        k_kmer_scan<true><<<scan_blocks_of(ctx, n), 256, 0, st>>>(sa);
         ctx->launches++;
     }
     FL_CUDA(ctx, ctx->sc_order.reserve(n_items, 0, st));
@@ -973,10 +1040,29 @@ static int score_kmer(fl_ctx *ctx, const BatchView &b) {
     return FL_OK;
 }
 
-int fl_score_view(fl_ctx *ctx, const BatchView &b) {
+int fl_score_complete(fl_ctx *ctx) {
+    if (!ctx->kmer_pending) return FL_OK;
+    ctx->kmer_pending = false;
+    const int slot = ctx->kmer_pending_slot;
+    ctx->kmer_pending_slot = -1;
+    FL_TRY(score_kmer_back(ctx, ctx->kmer_pending_view));
+    if (slot >= 0) {                                              // the staged inputs are free once these kernels have run
+        FL_CUDA(ctx, cudaEventRecord(ctx->stg[slot].consumed, ctx->stream));
+        ctx->stg[slot].in_use = true;
+    }
+    return FL_OK;
+}
+
+int fl_score_view(fl_ctx *ctx, const BatchView &b, bool defer) {
     if (b.n == 0) return FL_OK;
     if (ctx->kmers_count_stale || ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
     ctx->finalized = false;
     if (ctx->n_kmers == 0) return fl_score_phred(ctx, b);     // read.cpp:35: kmers->empty()
-    return score_kmer(ctx, b);
+    FL_TRY(score_kmer_front(ctx, b));
+    if (defer && (ctx->p.trim || ctx->p.split_set)) {
+        ctx->kmer_pending = true;
+        ctx->kmer_pending_view = b;
+        return FL_OK;
+    }
+    return score_kmer_back(ctx, b);
 }
