@@ -121,7 +121,6 @@ struct fl_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
-    int probe_wide = 0;        // dense sets: 8 table sectors in flight per thread (FL_PROBE_WIDE)
     int probe_mode = 2;        // load flavour of the bitmap probe (fl_score.cu; 2 = ld.global.nc.L1::no_allocate, measured best); FL_PROBE_MODE overrides
 
     // ---- Kmers ----
@@ -130,7 +129,12 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    int filter_kind = 2;                 // bit 1: load the filter with ld.global.cg (FL_FILTER_KIND); bit 0 (minimizer-keyed words) is a build-side experiment only
+    // Flavour of the pre-filter (fl_device.cuh): bit 1 = load it with ld.global.cg; bit 2 = one word per table group of four
+    // 16-mers; bit 3 = one word per pair of neighbours; bit 4 = four bits per member instead of two; bit 0 (minimizer-keyed
+    // words) is a build-side experiment only. -1 = chosen from the set's size when the set is finalised (fl_kmers_recount).
+    int filter_kind_request = -1;        // FL_FILTER_KIND
+    int filter_kind = 2;                 // the flavour in use
+    uint64_t filter_group4_max = 11000000, filter_pair_max = 22000000;   // largest sets keyed by group / by pair (FL_FILTER_G4_MAX, FL_FILTER_PAIR_MAX)
     bool use_filter = false;
     uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
     bool use_anchor = false;

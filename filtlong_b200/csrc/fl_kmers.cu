@@ -350,6 +350,16 @@ int fl_kmers_recount(fl_ctx *ctx) {
     // space) are probed directly.
     const size_t filter_words = (size_t)1 << ctx->filter_log2_words;
     ctx->use_filter = ctx->filter_enabled && ctx->n_kmers > 0 && ctx->n_kmers * (uint64_t)ctx->filter_min_bits_per_key <= filter_words * 64;
+    // Which flavour: the probe kernel is bound by L1TEX sector look-ups on a sparse set, one per filter word it loads, so a
+    // word shared by the four 16-mers of a table group (or by two neighbours) cuts them 4x (2x) -- at 4x (2x) the insertions.
+    // Small sets can afford that (false positives, each a wasted random HBM sector, stay below ~5 %); measured on the 20 M
+    // member set of config 3: pair-keyed 86 ms, per-16-mer 96-98 ms, group-keyed 109 ms (profiles/r02_probe_variants*.jsonl).
+    if (ctx->filter_kind_request >= 0) ctx->filter_kind = ctx->filter_kind_request;
+    else if (!ctx->anchor_enabled) ctx->filter_kind = 2 | 16;
+    else if (ctx->n_kmers <= ctx->filter_group4_max) ctx->filter_kind = 2 | 4 | 16;
+    else if (ctx->n_kmers <= ctx->filter_pair_max) ctx->filter_kind = 2 | 8 | 16;
+    else ctx->filter_kind = 2 | 16;
+    if (!ctx->anchor_enabled) ctx->filter_kind &= ~(4 | 8);        // the keyed flavours follow the anchored table's groups
     if (ctx->use_filter) {
         if (!ctx->d_filter) FL_CUDA(ctx, cudaMalloc(&ctx->d_filter, filter_words * sizeof(unsigned long long)));
         FL_CUDA(ctx, cudaMemsetAsync(ctx->d_filter, 0, filter_words * sizeof(unsigned long long), ctx->stream));

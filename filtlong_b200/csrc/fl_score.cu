@@ -47,7 +47,6 @@ struct ProbeArgs {
     unsigned filter_log2_words;
     int filter_kind;
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
-    uint32_t zero;                           // 0 (see WIDE)
 };
 
 // One 4-byte load from the 512 MiB membership bitmap per k-mer. The flavour of the load decides how
@@ -92,10 +91,11 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
     return __ldg(p);
 }
 
-// WIDE (dense sets, no pre-filter): all eight table sectors of a lane's 32 k-mers are requested before the first is looked
-// at (64 data registers, so 3 blocks per SM instead of 4, but 8 instead of ~4.5 sector requests in flight per thread)
-template <int MODE, int FILT, bool ANCH, bool WIDE = false>
-__global__ void __launch_bounds__(256, WIDE ? 3 : 4) k_probe_paint(ProbeArgs a) {
+// Measured and dropped (profiles/r02_probe_variants3_wide_and_4bit_filters.jsonl): a dense-set variant with all eight table
+// sectors of a lane requested up front (80 registers, 3 blocks per SM): 81.2 ms against 80.0 ms. The dense probe already sits at
+// the rate at which HBM serves random sectors (profiles/r02_sector_fetch_microbench_table_sizes.jsonl), not at a latency limit.
+template <int MODE, int FILT, bool ANCH>
+__global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
     const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
@@ -138,41 +138,6 @@ __global__ void __launch_bounds__(256, WIDE ? 3 : 4) k_probe_paint(ProbeArgs a) 
             long long nv = (long long)L - (FL_K - 1) - (long long)lb;
             const int nvalid = nv <= 0 ? 0 : (nv >= 32 ? 32 : (int)nv);
             uint32_t h = 0;
-            if (WIDE) {
-                uint32_t sec[8][8];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const uint32_t key = (fl_kmer_at(w, 4 * g + 3) >> 6) & 0x3FFFFFFu;
-                    if (4 * g < nvalid) {
-                        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                     : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                       "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                     : "l"(table + (size_t)key * 8u));
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
-                    }
-                }
-                // ptxas schedules the look-ups between the requests unless they depend on all eight: z is zero (a.zero is),
-                // but only the host knows
-                uint32_t z = sec[0][0];
-#pragma unroll
-                for (int g = 1; g < 8; ++g) z |= sec[g][0];
-                z &= a.zero;
-                LaneWords wz;
-                wz.w0 = w.w0 ^ z; wz.w1 = w.w1 ^ z; wz.w2 = w.w2 ^ z;
-#pragma unroll
-                for (int g = 0; g < 8; ++g) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int p = 4 * g + j;
-                        uint32_t word, bit;
-                        fl_anchor_slot(fl_kmer_at(wz, p), 3u - (unsigned)j, word, bit);
-                        const uint32_t v = (word & 1u) ? sec[g][2 * (3 - j) + 1] : sec[g][2 * (3 - j)];
-                        h |= (((v >> bit) & 1u) & (p < nvalid ? 1u : 0u)) << p;
-                    }
-                }
-            } else {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t words[16];
@@ -285,7 +250,6 @@ __global__ void __launch_bounds__(256, WIDE ? 3 : 4) k_probe_paint(ProbeArgs a) 
                     }
                 }
             }
-            }
             // paint: base covered if any of the 16 k-mers ending at or after it hit (read.cpp:53-54)
             uint32_t prev = __shfl_up_sync(0xffffffffu, h, 1);
             if (lane == 0) prev = carry;
@@ -384,6 +348,10 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
                 last = (wb + 31) * 32 + 32 - carry_open;
                 continue;
             }
+            if (nz == 0u) {                                      // 1024 uncovered bases: the open run just grows
+                carry_open += 1024;
+                continue;
+            }
             const unsigned lo_nz = nz & lower;
             const int j = lo_nz ? 31 - __clz(lo_nz) : 0;
             const int tz_j = __shfl_sync(0xffffffffu, tzc, j);
@@ -393,68 +361,82 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
             const bool is_first = x && !seen_one && !lo_nz;      // the run is [0, first): read.cpp:106-111 decides
             const bool b_emit = x && (is_first ? ((split_set && o >= split && o > 0) || (trim && o > 0))
                                                : (split_set && runlen >= split));
-            // zero runs strictly inside the word (shorter than 32: only a --split below 32 can want them)
-            int n_in = 0, in_last_e = 0;
-            if (split_set && split < 32 && x) {
-                uint32_t y = ~x & (0xFFFFFFFFu << lzc) & (0xFFFFFFFFu >> tzc);
-                while (y) {
-                    const int s0 = __ffs(y) - 1;
-                    const uint32_t rest = ~(y >> s0);
-                    const int ln = __ffs(rest) - 1;              // run length (a one-bit follows inside the word)
-                    if (ln >= split) { ++n_in; in_last_e = wi * 32 + s0 + ln; }
-                    y &= ~(((1u << ln) - 1u) << s0);
+            if (!(split_set && split < 32)) {
+                // bad ranges end only where a word has its lowest one-bit: at most one per lane, counted with ballots
+                const unsigned em = __ballot_sync(0xffffffffu, b_emit);
+                if (em) {
+                    const unsigned lo_em = em & lower;
+                    const int prev_e = __shfl_sync(0xffffffffu, o, lo_em ? 31 - __clz(lo_em) : 0);
+                    const int rs_mine = lo_em ? prev_e : rs;
+                    const bool b_child = b_emit && z - rs_mine > 0;
+                    const unsigned cm = __ballot_sync(0xffffffffu, b_child);
+                    if (EMIT && b_child) child(rs_mine, z, n_child + __popc(cm & lower));
+                    n_bad += __popc(em);
+                    n_child += __popc(cm);
+                    rs = __shfl_sync(0xffffffffu, o, 31 - __clz(em));
                 }
-            }
-            const bool emits = b_emit || n_in > 0;
-            const int my_last_e = n_in > 0 ? in_last_e : o;
-            const unsigned em = __ballot_sync(0xffffffffu, emits);
-            const unsigned lo_em = em & lower;
-            const int pe = lo_em ? 31 - __clz(lo_em) : 0;
-            const int prev_e = __shfl_sync(0xffffffffu, my_last_e, pe);
-            const int rs_mine = lo_em ? prev_e : rs;
-            const int b_child = (b_emit && z - rs_mine > 0) ? 1 : 0;
-            const int my_children = b_child + n_in;              // every in-word run is preceded by a one-bit: a child always
-            int incl = my_children;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (unsigned)d) incl += t;
-            }
-            if (EMIT && emits) {
-                int idx = n_child + incl - my_children, prev = rs_mine;
-                if (b_emit) {
-                    if (b_child) child(prev, z, idx++);
-                    prev = o;
-                }
-                if (n_in > 0) {
+            } else {
+                // zero runs strictly inside the word (shorter than 32: only a --split below 32 can want them)
+                int n_in = 0, in_last_e = 0;
+                if (split_set && split < 32 && x) {
                     uint32_t y = ~x & (0xFFFFFFFFu << lzc) & (0xFFFFFFFFu >> tzc);
                     while (y) {
                         const int s0 = __ffs(y) - 1;
                         const uint32_t rest = ~(y >> s0);
-                        const int ln = __ffs(rest) - 1;
-                        if (ln >= split) {
-                            child(prev, wi * 32 + s0, idx++);
-                            prev = wi * 32 + s0 + ln;
-                        }
+                        const int ln = __ffs(rest) - 1;              // run length (a one-bit follows inside the word)
+                        if (ln >= split) { ++n_in; in_last_e = wi * 32 + s0 + ln; }
                         y &= ~(((1u << ln) - 1u) << s0);
                     }
                 }
-            }
-            int my_bad = (b_emit ? 1 : 0) + n_in;
+                const bool emits = b_emit || n_in > 0;
+                const int my_last_e = n_in > 0 ? in_last_e : o;
+                const unsigned em = __ballot_sync(0xffffffffu, emits);
+                const unsigned lo_em = em & lower;
+                const int pe = lo_em ? 31 - __clz(lo_em) : 0;
+                const int prev_e = __shfl_sync(0xffffffffu, my_last_e, pe);
+                const int rs_mine = lo_em ? prev_e : rs;
+                const int b_child = (b_emit && z - rs_mine > 0) ? 1 : 0;
+                const int my_children = b_child + n_in;              // every in-word run is preceded by a one-bit: a child always
+                int incl = my_children;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) my_bad += __shfl_xor_sync(0xffffffffu, my_bad, d);
-            n_bad += my_bad;
-            n_child += __shfl_sync(0xffffffffu, incl, 31);
-            if (em) rs = __shfl_sync(0xffffffffu, my_last_e, 31 - __clz(em));
-            if (nz) {
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (unsigned)d) incl += t;
+                }
+                if (EMIT && emits) {
+                    int idx = n_child + incl - my_children, prev = rs_mine;
+                    if (b_emit) {
+                        if (b_child) child(prev, z, idx++);
+                        prev = o;
+                    }
+                    if (n_in > 0) {
+                        uint32_t y = ~x & (0xFFFFFFFFu << lzc) & (0xFFFFFFFFu >> tzc);
+                        while (y) {
+                            const int s0 = __ffs(y) - 1;
+                            const uint32_t rest = ~(y >> s0);
+                            const int ln = __ffs(rest) - 1;
+                            if (ln >= split) {
+                                child(prev, wi * 32 + s0, idx++);
+                                prev = wi * 32 + s0 + ln;
+                            }
+                            y &= ~(((1u << ln) - 1u) << s0);
+                        }
+                    }
+                }
+                int my_bad = (b_emit ? 1 : 0) + n_in;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) my_bad += __shfl_xor_sync(0xffffffffu, my_bad, d);
+                n_bad += my_bad;
+                n_child += __shfl_sync(0xffffffffu, incl, 31);
+                if (em) rs = __shfl_sync(0xffffffffu, my_last_e, 31 - __clz(em));
+            }
+            {
                 const int top = 31 - __clz(nz);
                 const int tz_top = __shfl_sync(0xffffffffu, tzc, top);
                 carry_open = tz_top + 32 * (31 - top);
                 last = (wb + top) * 32 + 32 - tz_top;                                       // read.cpp:81-84
                 if (!seen_one) first = __shfl_sync(0xffffffffu, o, __ffs(nz) - 1);          // read.cpp:77-80
                 seen_one = true;
-            } else {
-                carry_open += 1024;
             }
         }
         // the tail [last, L) and the closing child (read.cpp:112-116, 127-129)
@@ -946,9 +928,6 @@ static int score_kmer_front(fl_ctx *ctx, const BatchView &b) {
                     else if (filt == 1) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa);
                     else if (filt == 2) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa);
                     else k_probe_paint<4, 3, true><<<blocks, 256, 0, st>>>(pa);
-                } else if (filt == 0 && ctx->probe_wide) {
-                    const unsigned wide_blocks = blocks < (unsigned)ctx->sm_count * 3 ? blocks : (unsigned)ctx->sm_count * 3;
-                    k_probe_paint<2, 0, true, true><<<wide_blocks, 256, 0, st>>>(pa);
                 } else {
                     if (filt == 0) k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
                     else if (filt == 1) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
