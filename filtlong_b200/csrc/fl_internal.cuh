@@ -134,7 +134,7 @@ struct fl_ctx {
     // words) is a build-side experiment only. -1 = chosen from the set's size when the set is finalised (fl_kmers_recount).
     int filter_kind_request = -1;        // FL_FILTER_KIND
     int filter_kind = 2;                 // the flavour in use
-    uint64_t filter_group4_max = 11000000, filter_pair_max = 22000000;   // largest sets keyed by group / by pair (FL_FILTER_G4_MAX, FL_FILTER_PAIR_MAX)
+    uint64_t filter_group4_max = 6000000, filter_pair_max = 22000000;   // largest sets keyed by group / by pair (FL_FILTER_G4_MAX, FL_FILTER_PAIR_MAX)
     bool use_filter = false;
     uint32_t *d_anchor = nullptr;        // position-anchored membership table (2 GiB), see fl_anchor_slot
     bool use_anchor = false;

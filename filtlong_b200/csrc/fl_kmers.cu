@@ -352,8 +352,9 @@ int fl_kmers_recount(fl_ctx *ctx) {
     ctx->use_filter = ctx->filter_enabled && ctx->n_kmers > 0 && ctx->n_kmers * (uint64_t)ctx->filter_min_bits_per_key <= filter_words * 64;
     // Which flavour: the probe kernel is bound by L1TEX sector look-ups on a sparse set, one per filter word it loads, so a
     // word shared by the four 16-mers of a table group (or by two neighbours) cuts them 4x (2x) -- at 4x (2x) the insertions.
-    // Small sets can afford that (false positives, each a wasted random HBM sector, stay below ~5 %); measured on the 20 M
-    // member set of config 3: pair-keyed 86 ms, per-16-mer 96-98 ms, group-keyed 109 ms (profiles/r02_probe_variants*.jsonl).
+    // Small sets can afford that (false positives, each a wasted random HBM sector, stay below ~5 %). Measured, probe ms of
+    // config 3's reads against sets of 5 / 10 / 15 / 20 M members (profiles/r02_probe_variants4_filter_flavour_by_set_size.jsonl):
+    // per-16-mer 92 / 93 / - / 95, pair-keyed 66 / 68 / 76 / 87, group-keyed 64 / 77 / 100 / 109.
     if (ctx->filter_kind_request >= 0) ctx->filter_kind = ctx->filter_kind_request;
     else if (!ctx->anchor_enabled) ctx->filter_kind = 2 | 16;
     else if (ctx->n_kmers <= ctx->filter_group4_max) ctx->filter_kind = 2 | 4 | 16;

@@ -684,6 +684,7 @@ __global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
             KwAnchor an;
             kw_set_anchor(an, k, best, c);
             int cmin = c, trec = c;                                // lowest / highest after-step count of the current epoch
+            int H = 0, H_trec = -0x7FFFFFFF;                       // cached epoch limit and the record level it was computed for
             // inside the loop the NEXT iteration's words are requested before this iteration's (dependent) arithmetic
             // starts: one memory latency per 1024 steps would otherwise be all a warp does
             for (int t0 = 0; t0 < T; t0 += 1024) {
@@ -739,12 +740,16 @@ __global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
                 int cur = 0;
                 for (;;) {
                     // first level whose first visit ends the epoch: beyond the anchor's binade, or inside an edge interval
-                    int H = an.c_edge + 1;
-                    for (int i = 0; i < k.n_edges; ++i)
-                        if (k.ehi[i] >= trec) {
-                            const int h = k.elo[i] > trec + 1 ? k.elo[i] : trec + 1;
-                            H = h < H ? h : H;
-                        }
+                    // (a function of the anchor and of the record level: both change rarely, so it is kept across iterations)
+                    if (H_trec != trec) {
+                        H = an.c_edge + 1;
+                        for (int i = 0; i < k.n_edges; ++i)
+                            if (k.ehi[i] >= trec) {
+                                const int h = k.elo[i] > trec + 1 ? k.elo[i] : trec + 1;
+                                H = h < H ? h : H;
+                            }
+                        H_trec = trec;
+                    }
                     const bool in_range = valid && (int)lane >= cur;
                     const bool flag = in_range && ((an.unsafe && differs) || hi_level >= H);
                     const unsigned fm = __ballot_sync(0xffffffffu, flag);
@@ -774,6 +779,7 @@ __global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
                     kw_set_anchor(an, k, w, cw);
                     cmin = cw;
                     trec = cw;
+                    H_trec = -0x7FFFFFFF;                          // new anchor: the limit must be recomputed
                     cur = first + 1;
                 }
                 c += __shfl_sync(0xffffffffu, incl, 31);
