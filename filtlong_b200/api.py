@@ -148,6 +148,12 @@ class Context:
     def kmers_release_build_state(self):
         self._ck(self.L.fl_kmers_release_build_state(self.h), "fl_kmers_release_build_state")
 
+    def kmers_probe_info(self):
+        """(pre-filter in use, its flavour bits, log2 of its words, anchored table in use): fl_kmers_probe_info."""
+        info = (C.c_int32 * 4)()
+        self._ck(self.L.fl_kmers_probe_info(self.h, info), "fl_kmers_probe_info")
+        return dict(pre_filter=bool(info[0]), filter_kind=int(info[1]), filter_log2_words=int(info[2]), anchored=bool(info[3]))
+
     # ---- sharded read set (one context per GPU, NCCL behind the C ABI) ----
     @staticmethod
     def comm_unique_id():

@@ -130,6 +130,7 @@ SYMBOLS = [
     ("fl_kmers_bitmap_dev", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("fl_kmers_bitmap_changed", C.c_int, [_P]),
     ("fl_kmers_release_build_state", C.c_int, [_P]),
+    ("fl_kmers_probe_info", C.c_int, [_P, C.POINTER(C.c_int32)]),
     ("fl_reads_push", C.c_int, [_P, C.POINTER(Batch)]),
     ("fl_reads_push_text", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.POINTER(TextRecords), C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),

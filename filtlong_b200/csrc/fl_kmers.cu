@@ -441,6 +441,17 @@ extern "C" int fl_kmers_bitmap_changed(fl_ctx *ctx) {
     return FL_OK;
 }
 
+extern "C" int fl_kmers_probe_info(fl_ctx *ctx, int32_t info[4]) {
+    FL_ENTER(ctx);
+    if (!info) return FL_EINVAL;
+    if (ctx->kmers_count_stale || ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));
+    info[0] = ctx->use_filter ? 1 : 0;
+    info[1] = ctx->filter_kind;
+    info[2] = (int32_t)ctx->filter_log2_words;
+    info[3] = ctx->use_anchor ? 1 : 0;
+    return FL_OK;
+}
+
 extern "C" int fl_kmers_release_build_state(fl_ctx *ctx) {
     FL_ENTER(ctx);
     if (ctx->multi_pending) FL_TRY(fl_kmers_recount(ctx));

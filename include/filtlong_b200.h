@@ -146,11 +146,18 @@ int fl_kmers_bitmap_dev(fl_ctx *ctx, void **dev_ptr, uint64_t *n_bytes);
 int fl_kmers_bitmap_changed(fl_ctx *ctx);
 /* Releases the transient multiple-copy build state (counters, first-seen times, Bloom times). */
 int fl_kmers_release_build_state(fl_ctx *ctx);
+/* How the finalised set is laid out for the probe kernel (diagnostics / measurement): info[0] = a pre-filter is in use,
+ * info[1] = its flavour (bit 2: one word per table group of four 16-mers, bit 3: one word per pair, bit 4: four bits per
+ * member), info[2] = log2 of its 64-bit words, info[3] = the position-anchored table is in use. */
+int fl_kmers_probe_info(fl_ctx *ctx, int32_t info[4]);
 
 /* ---- Read: per-read scoring (src/read.cpp:25-144) ------------------------------------------ */
 /* Scores a batch the way one `new Read(...)` per record does (main.cpp:108) and appends the
  * result rows to the context. Mode = Phred if the k-mer set is empty, k-mer otherwise
- * (read.cpp:35). Host buffers: copies are issued inside the call. */
+ * (read.cpp:35). Host buffers: copies are issued inside the call and the buffers may be reused when it
+ * returns. In k-mer mode with --trim / --split the batch's rows are completed at the start of the next
+ * call on the context, whichever it is (the row count costs a host round trip, which is paid once the next
+ * batch's copy is under way); fl_reads_count, fl_finalize, fl_results_* ... all see the batch. */
 int fl_reads_push(fl_ctx *ctx, const fl_batch *host_batch);
 /* Same with the arena already resident in device memory (no copies). */
 int fl_reads_push_device(fl_ctx *ctx, const fl_batch *dev_batch);
