@@ -344,6 +344,36 @@ def test_bloom_false_positive_kat_912k_reads():
     assert n == 25225
 
 
+def test_prefilter_flavour_follows_the_set_size_and_all_flavours_agree(monkeypatch):
+    """fl_kmers_recount picks the pre-filter's flavour from the number of members (one word per table group of four 16-mers for
+    small sets, per pair of neighbours, per 16-mer); forcing each of them (FL_FILTER_KIND), or no filter, must not change a bit."""
+    rng, genome, genome_n, reads = make_kmer_case(77, n_reads=120)
+    opts = dict(keep_percent=85.0, trim=True, split=120)
+    outs = {}
+    for tag, env in (("auto", {}), ("group", {"FL_FILTER_KIND": "22"}), ("pair", {"FL_FILTER_KIND": "26"}), ("single", {"FL_FILTER_KIND": "18"}),
+                     ("two_bits", {"FL_FILTER_KIND": "2"}), ("none", {"FL_FILTER": "0"}), ("pair_forced_by_size", {"FL_FILTER_G4_MAX": "10"})):
+        for k in ("FL_FILTER_KIND", "FL_FILTER", "FL_FILTER_G4_MAX"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = api.Context(api.make_params(**opts))
+        ctx.kmers_add([genome_n], False)
+        info = ctx.kmers_probe_info()
+        hb = api.HostBatch([r[0] for r in reads], [r[1] for r in reads])
+        ctx.push(hb)
+        summ = ctx.finalize(hb.total_bases)
+        rw = ctx.row_results()
+        outs[tag] = (info, summ.keeping, {k: v.tobytes() for k, v in rw.items()})
+        ctx.close()
+    assert outs["auto"][0]["pre_filter"] and outs["auto"][0]["filter_kind"] & 4          # 120 k members: keyed by table group
+    assert outs["pair_forced_by_size"][0]["filter_kind"] & 8
+    assert not outs["none"][0]["pre_filter"]
+    assert all(i["anchored"] for i, _, _ in outs.values())
+    ref = outs["none"]
+    for tag, o in outs.items():
+        assert o[1:] == ref[1:], tag
+
+
 def test_kmer_results_do_not_depend_on_batching():
     """fl_reads_push double-buffers its staging (copy of batch i+1 overlaps the kernels of batch
     i): pushing the same reads as 1, 3 or 7 batches must give identical rows."""
