@@ -153,10 +153,11 @@ struct Shard {
 };
 
 struct Ring {
-    static constexpr int K = 8;                 // slots = reader threads per shard
-    char *slot[K] = {nullptr};
-    bool registered[K] = {false};
-    int state[K] = {0};                         // 0 free, 1 filled, -1 the reader failed
+    static constexpr int KMAX = 32;
+    int K = 8;                                  // slots = reader threads per shard (FL_READERS)
+    char *slot[KMAX] = {nullptr};
+    bool registered[KMAX] = {false};
+    int state[KMAX] = {0};                      // 0 free, 1 filled, -1 the reader failed
     std::mutex m;
     std::condition_variable cv;
 };
@@ -171,19 +172,23 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
                const unsigned char *comm_id, const std::function<fl_ctx *()> &get_ctx0, std::atomic<bool> &abort_all, uint64_t slot_bytes,
                bool share_kmers) {
     Ring ring;
+    if (const char *e = getenv("FL_READERS")) {
+        const int k = atoi(e);
+        ring.K = k < 1 ? 1 : (k > ring.KMAX ? ring.KMAX : k);
+    }
     std::vector<std::thread> readers;
     try {
         // reader threads first: pread() from the page cache needs neither CUDA nor page faults on a mapping.
         // Chunk i of the shard goes through slot i % K.
         const size_t n_chunks = sh.chunk_hi - sh.chunk_lo;
-        for (int k = 0; k < Ring::K; ++k) {
+        for (int k = 0; k < ring.K; ++k) {
             void *p = nullptr;
             if (posix_memalign(&p, 2u << 20, (size_t)slot_bytes + 4096) != 0) throw std::runtime_error("chunk ring: out of memory");
             ring.slot[k] = (char *)p;
         }
-        for (int k = 0; k < Ring::K; ++k)
+        for (int k = 0; k < ring.K; ++k)
             readers.emplace_back([&, k] {
-                for (size_t i = (size_t)k; i < n_chunks; i += Ring::K) {
+                for (size_t i = (size_t)k; i < n_chunks; i += ring.K) {
                     {
                         std::unique_lock<std::mutex> lk(ring.m);
                         ring.cv.wait(lk, [&] { return ring.state[k] == 0 || abort_all.load(); });
@@ -212,7 +217,7 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
             sh.owns_ctx = true;
         }
         check(sh.ctx, fl_ctx_set_params(sh.ctx, &params), "fl_ctx_set_params");
-        for (int k = 0; k < Ring::K; ++k) ring.registered[k] = fl_host_register(ring.slot[k], slot_bytes + 4096) == FL_OK;
+        for (int k = 0; k < ring.K; ++k) ring.registered[k] = fl_host_register(ring.slot[k], slot_bytes + 4096) == FL_OK;
         if (nranks > 1) {
             check(sh.ctx, fl_comm_init(sh.ctx, comm_id, sh.index, nranks), "fl_comm_init");
             if (share_kmers) {
@@ -223,7 +228,7 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
         }
         size_t guess = 1024;
         for (size_t i = 0; i < n_chunks && !abort_all.load(); ++i) {
-            const int k = (int)(i % Ring::K);
+            const int k = (int)(i % ring.K);
             {
                 std::unique_lock<std::mutex> lk(ring.m);
                 ring.cv.wait(lk, [&] { return ring.state[k] != 0 || abort_all.load(); });
@@ -267,7 +272,7 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
     }
     ring.cv.notify_all();
     for (auto &t : readers) t.join();
-    for (int k = 0; k < Ring::K; ++k) {
+    for (int k = 0; k < ring.K; ++k) {
         if (ring.registered[k]) fl_host_unregister(ring.slot[k]);
         free(ring.slot[k]);
     }
