@@ -94,6 +94,7 @@ __device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, u
 // Measured and dropped (profiles/r02_probe_variants3_wide_and_4bit_filters.jsonl): a dense-set variant with all eight table
 // sectors of a lane requested up front (80 registers, 3 blocks per SM): 81.2 ms against 80.0 ms. The dense probe already sits at
 // the rate at which HBM serves random sectors (profiles/r02_sector_fetch_microbench_table_sizes.jsonl), not at a latency limit.
+// (compiled for 5 / 6 blocks per SM the pair-keyed variant spills and runs in 94 / 115 ms against 86: profiles/r02_probe_variants5_blocks_per_sm.jsonl)
 template <int MODE, int FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
