@@ -761,26 +761,50 @@ __global__ void __launch_bounds__(256, 4) k_kmer_window(WinArgs a) {
                     cmin = seg_min < cmin ? seg_min : cmin;
                     trec = seg_max > trec ? seg_max : trec;
                     if (first == 32) break;
-                    // close the epoch, then walk the flagged word with the reference's own operations
-                    const double f = kw_eval(an, k, cmin);
-                    best = f < best ? f : best;
-                    int cw = __shfl_sync(0xffffffffu, cs, first);
-                    double w = kw_eval(an, k, cw);
+                    // The flagged word, one lane per step. Only the step that does something irreversible is done with the
+                    // reference's own operations: the first one that reaches the level H (or, from an odd value in a tie
+                    // binade, the first that does anything). The steps before it are still inside the epoch (F), the steps
+                    // after it belong to the epoch of the new anchor -- which may end in this very word again.
                     {
                         const uint32_t win = __shfl_sync(0xffffffffu, in, first), wout = __shfl_sync(0xffffffffu, out, first);
-                        uint32_t todo = win | wout;
-                        while (todo) {
-                            const int t = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            if ((wout >> t) & 1u) { w -= k.rq; --cw; }     // read.cpp:229 (w -= 0.0 changes nothing)
-                            if ((win >> t) & 1u) { w += k.rq; ++cw; }      // read.cpp:230
-                            best = w < best ? w : best;                    // read.cpp:231-232
+                        const int cw0 = __shfl_sync(0xffffffffu, cs, first);
+                        const uint32_t upto = 0xFFFFFFFFu >> (31u - lane);             // steps 0 .. lane
+                        const int lvl = cw0 + __popc(win & ~wout & upto) - __popc(wout & ~win & upto);   // level after step `lane`
+                        int p = 0;
+                        for (;;) {
+                            if (H_trec != trec) {
+                                H = an.c_edge + 1;
+                                for (int i = 0; i < k.n_edges; ++i)
+                                    if (k.ehi[i] >= trec) {
+                                        const int h = k.elo[i] > trec + 1 ? k.elo[i] : trec + 1;
+                                        H = h < H ? h : H;
+                                    }
+                                H_trec = trec;
+                            }
+                            const bool stop = (int)lane >= p && (an.unsafe ? (((win | wout) >> lane) & 1u) != 0u : lvl >= H);
+                            const unsigned sm = __ballot_sync(0xffffffffu, stop);
+                            const int ts = sm ? __ffs(sm) - 1 : 32;
+                            const bool before = (int)lane >= p && (int)lane < ts;
+                            const int smin = __reduce_min_sync(0xffffffffu, before ? lvl : 0x7FFFFFFF);
+                            const int smax = __reduce_max_sync(0xffffffffu, before ? lvl : -0x7FFFFFFF);
+                            cmin = smin < cmin ? smin : cmin;
+                            trec = smax > trec ? smax : trec;
+                            if (ts == 32) break;
+                            const double f = kw_eval(an, k, cmin);                       // close the epoch
+                            best = f < best ? f : best;
+                            int cw = __shfl_sync(0xffffffffu, lvl, ts > 0 ? ts - 1 : 0);
+                            if (ts == 0) cw = cw0;
+                            double w = kw_eval(an, k, cw);                               // the chain's value before step ts
+                            if ((wout >> ts) & 1u) { w -= k.rq; --cw; }                  // read.cpp:229
+                            if ((win >> ts) & 1u) { w += k.rq; ++cw; }                   // read.cpp:230
+                            best = w < best ? w : best;                                  // read.cpp:231-232
+                            kw_set_anchor(an, k, w, cw);
+                            cmin = cw;
+                            trec = cw;
+                            H_trec = -0x7FFFFFFF;                                        // new anchor: the limit must be recomputed
+                            p = ts + 1;
                         }
                     }
-                    kw_set_anchor(an, k, w, cw);
-                    cmin = cw;
-                    trec = cw;
-                    H_trec = -0x7FFFFFFF;                          // new anchor: the limit must be recomputed
                     cur = first + 1;
                 }
                 c += __shfl_sync(0xffffffffu, incl, 31);

@@ -208,22 +208,45 @@ double kmer_window_model(const uint32_t *mask, int S, int E, int ws, long long *
             continue;
         }
         ++n_slow;
-        {   /* close the epoch, then walk the word with the reference's own operations */
-            const double f = eval_F(&a, &k, cmin, &n_true);
-            if (f < best) best = f;
+        /* Only the step that does something irreversible is done with the reference's own operations: the first step that
+         * reaches a level whose first visit ends the epoch (or, from an odd value in a tie binade, the first step that does
+         * anything). Everything before it in the word is still inside the epoch (F), everything after it belongs to the
+         * epoch of the new anchor -- which may end in this very word again. */
+        {
+            int p = 0, level = c;                                      /* next step to look at, level before it */
+            for (;;) {
+                int ts = -1, lv = level, seg_min = 0x7FFFFFFF, seg_max = -0x7FFFFFFF, rec = trec;
+                for (int t = p; t < 32; ++t) {
+                    const int o = (int)((out >> t) & 1u), i = (int)((in >> t) & 1u);
+                    const int after = lv - o + i;
+                    int stop;
+                    if (a.unsafe) stop = o | i;
+                    else stop = after > rec && (after > a.c_edge || touches_edge(&k, after, after));
+                    if (stop) { ts = t; break; }
+                    lv = after;
+                    if (lv < seg_min) seg_min = lv;
+                    if (lv > seg_max) seg_max = lv;
+                    if (lv > rec) rec = lv;
+                }
+                if (seg_min < cmin) cmin = seg_min;
+                if (seg_max > trec) trec = seg_max;
+                if (ts < 0) { level = lv; break; }
+                {
+                    const double f = eval_F(&a, &k, cmin, &n_true);        /* close the epoch */
+                    if (f < best) best = f;
+                }
+                double w = eval_F(&a, &k, lv, &n_true);                   /* the chain's value before step ts */
+                if ((out >> ts) & 1u) { w -= k.rq; --lv; ++n_true; }      /* read.cpp:229 */
+                if ((in >> ts) & 1u) { w += k.rq; ++lv; ++n_true; }       /* read.cpp:230 */
+                if (w < best) best = w;                                   /* read.cpp:231-232 */
+                set_anchor(&a, &k, w, lv);
+                cmin = lv;
+                trec = lv;
+                level = lv;
+                p = ts + 1;
+            }
+            c = level;
         }
-        double w = eval_F(&a, &k, c, &n_true);
-        uint32_t todo = in | out;
-        while (todo) {
-            const int t = __builtin_ctz(todo);
-            todo &= todo - 1;
-            if ((out >> t) & 1) { w -= k.rq; --c; ++n_true; }          /* read.cpp:229 (w -= 0.0 changes nothing) */
-            if ((in >> t) & 1) { w += k.rq; ++c; ++n_true; }           /* read.cpp:230 */
-            if (w < best) best = w;
-        }
-        set_anchor(&a, &k, w, c);
-        cmin = c;
-        trec = c;
     }
     {
         const double f = eval_F(&a, &k, cmin, &n_true);
