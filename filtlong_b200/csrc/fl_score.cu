@@ -481,8 +481,8 @@ __global__ void __launch_bounds__(256) k_kmer_scan(ScanArgs a) {
 //  (4) not reversible: an addition that reaches a level not visited since the anchor AND next to a binade edge
 //      (it enters the coarser grid above, or leaves the binade's lowest level), and an ODD value inside a tie
 //      binade (the first after entering from the finer grid below, or w0 itself) until an operation made it even.
-//      A 32-step word that does either is walked with the reference's own double operations and a new epoch
-//      starts from the value it produced. Rare: a few record levels per row.
+//      Only THAT step is done with the reference's own double operations (its word is spread over the warp, one lane
+//      per step, to find it); a new epoch starts from the value it produced. Rare: a few record levels per row.
 // tests/models/kmer_window_model.c is the scalar model of exactly this procedure (fuzzed against the reference
 // recurrence: tests/test_kmer_window_model.py); the kernel below is its transcription, 32 words per iteration.
 // ---------------------------------------------------------------------------------------------

@@ -20,12 +20,14 @@
  *      low bit) or leaves the binade's lowest level (the subtraction that would undo it falls through the
  *      floor onto the finer grid); a new epoch starts from the value it produced. And an ODD value inside a tie
  *      binade (the first one after entering from the finer grid below, or w0 itself): nothing is reversible
- *      until an operation has made it even. Words of 32 steps that do either are walked with true double
- *      operations; they are rare (a handful of record levels per row).
+ *      until an operation has made it even. Only THAT step is done with true double operations (the chain's
+ *      value before it is F, the value after it is the new anchor); such steps are rare (a handful of record
+ *      levels per row).
  *
  * The model processes a row in words of 32 steps exactly like one lane of the kernel does (word statistics
- * from a nibble look-up table, a predicate that flags the word, a scalar walk only if flagged), so that the
- * CUDA code is a transcription of this file.
+ * from a nibble look-up table, a predicate that flags the word; a flagged word is searched for its
+ * irreversible step(s), which the kernel does with one lane per step), so that the CUDA code is a transcription
+ * of this file.
  */
 #include <math.h>
 #include <stdint.h>
