@@ -62,28 +62,15 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     }
     c->stream = c->own_stream;
     // tuning knobs for profiling runs (defaults are the measured best, see profiles/ and DESIGN.md section 7)
-    if (const char *m = getenv("FL_PROBE_MODE")) c->probe_mode = atoi(m);
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
     if (const char *f = getenv("FL_ANCHOR")) c->anchor_enabled = atoi(f);
     if (const char *f = getenv("FL_PHRED_MODE")) c->phred_mode = atoi(f);
     if (const char *f = getenv("FL_PHRED_OCC")) c->phred_occupancy = atoi(f);
-    {
-        const char *pe = getenv("FL_L2_PERSIST");
-        if (pe && atoi(pe) != 0) {   // off by default: measured slower (the set-aside shrinks the normal L2)
-            size_t want = (size_t)prop.persistingL2CacheMaxSize;
-            if (want > ((size_t)96 << 20)) want = (size_t)96 << 20;
-            if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-                c->l2_persist_bytes = want;
-                c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-            }
-        }
-    }
     if (const char *f = getenv("FL_FILTER_LOG2_WORDS")) c->filter_log2_words = (unsigned)atoi(f);
     if (const char *f = getenv("FL_FILTER_KIND")) c->filter_kind_request = atoi(f);
     if (const char *f = getenv("FL_FILTER_G4_MAX")) c->filter_group4_max = (uint64_t)atoll(f);
     if (const char *f = getenv("FL_FILTER_PAIR_MAX")) c->filter_pair_max = (uint64_t)atoll(f);
     if (const char *f = getenv("FL_FILTER_MIN_BITS")) c->filter_min_bits_per_key = atoi(f);
-    if (const char *g = getenv("FL_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     *out = c;
     return FL_OK;
 }

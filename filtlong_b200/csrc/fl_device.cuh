@@ -112,22 +112,11 @@ __host__ __device__ __forceinline__ void fl_anchor_slot(uint32_t kmer, unsigned 
     bit = rest & 31u;
 }
 
-// L2-resident pre-filter in front of the 512 MiB bitmap (fl_kmers.cu / fl_score.cu): two bits in ONE
-// 64-bit word of a 2^log2_words-word table. No false negatives, so "filter says absent" is final.
-// kind 1 picks the WORD from the k-mer's minimizer (smallest hashed 11-mer of its six): consecutive
-// k-mers of a read mostly share it, so a lane's successive filter loads hit the same word (L1) and
-// the L2 sees ~3x fewer requests; the two bit positions still come from the whole k-mer.
+// L2-resident pre-filter in front of the membership tables (fl_kmers.cu / fl_score.cu): two bits (kind bit 4: four)
+// in ONE 64-bit word of a 2^log2_words-word table. No false negatives, so "filter says absent" is final.
+// This is the flavour with one word per 16-mer; the keyed flavours follow.
 __device__ __forceinline__ void fl_filter_slot(uint32_t kmer, unsigned log2_words, int kind, uint32_t &word, unsigned long long &bits) {
-    uint32_t h1 = kmer * 0x9E3779B1u;
-    if (kind & 1) {
-        h1 = 0xFFFFFFFFu;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const uint32_t m = ((kmer >> (2 * i)) & 0x3FFFFFu) * 0x9E3779B1u;
-            h1 = m < h1 ? m : h1;
-        }
-        h1 *= 0x85EBCA6Bu;                      // spread the (small) minimum over the word index range
-    }
+    const uint32_t h1 = kmer * 0x9E3779B1u;
     const uint32_t h2 = (kmer ^ (kmer >> 15)) * 0x85EBCA6Bu;
     word = h1 >> (32 - log2_words);
     bits = (1ull << (h2 >> 26)) | (1ull << ((h2 >> 20) & 63u));

@@ -121,7 +121,6 @@ struct fl_ctx {
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;
-    int probe_mode = 2;        // load flavour of the bitmap probe (fl_score.cu; 2 = ld.global.nc.L1::no_allocate, measured best); FL_PROBE_MODE overrides
 
     // ---- Kmers ----
     uint32_t *d_bitmap = nullptr;        // 2^32 bits, direct-address membership
@@ -129,9 +128,9 @@ struct fl_ctx {
     // optional L2-resident pre-filter of the set (built when the set is small enough to make it selective)
     unsigned long long *d_filter = nullptr;
     unsigned filter_log2_words = 22;     // 2^22 x 8 B = 32 MiB (measured best on B200: 64 MiB no longer stays in L2)
-    // Flavour of the pre-filter (fl_device.cuh): bit 1 = load it with ld.global.cg; bit 2 = one word per table group of four
-    // 16-mers; bit 3 = one word per pair of neighbours; bit 4 = four bits per member instead of two; bit 0 (minimizer-keyed
-    // words) is a build-side experiment only. -1 = chosen from the set's size when the set is finalised (fl_kmers_recount).
+    // Flavour of the pre-filter (fl_device.cuh): bit 2 = one word per table group of four 16-mers; bit 3 = one word per pair
+    // of neighbours; bit 4 = four bits per member instead of two (bits 0 and 1 are unused: former experiments). -1 = chosen
+    // from the set's size when the set is finalised (fl_kmers_recount).
     int filter_kind_request = -1;        // FL_FILTER_KIND
     int filter_kind = 2;                 // the flavour in use
     uint64_t filter_group4_max = 6000000, filter_pair_max = 22000000;   // largest sets keyed by group / by pair (FL_FILTER_G4_MAX, FL_FILTER_PAIR_MAX)
@@ -141,7 +140,6 @@ struct fl_ctx {
     int anchor_enabled = 1;              // FL_ANCHOR=0 probes the bitmap itself (profiling, cross-checks)
     int filter_enabled = 1;              // FL_FILTER=0 disables (profiling)
     int filter_min_bits_per_key = 8;     // the filter is used while it has at least this many bits per member
-    size_t l2_persist_bytes = 0, l2_window_max = 0;   // persisting-L2 set-aside granted to this context
     bool kmers_count_stale = false;
     // multiple-copy build state (kmers.cpp:142-166 in closed form, see fl_kmers.cu)
     uint32_t *d_seen[4] = {nullptr, nullptr, nullptr, nullptr};   // ">= 1,2,3,4 sightings" bitmaps

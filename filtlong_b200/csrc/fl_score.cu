@@ -49,23 +49,10 @@ struct ProbeArgs {
     uint32_t *mask;                          // 1 bit per padded base, same coordinates as the arena
 };
 
-// One 4-byte load from the 512 MiB membership bitmap per k-mer. The flavour of the load decides how
-// much HBM traffic a random probe costs (measured with ncu, profiles/): MODE 0 = ld.global.nc (L1
-// allocates and pulls whole 128-byte lines), 1 = ld.global.cg (L2 only, sector granular),
-// 2 = ld.global.nc.L1::no_allocate.
-// MODE 3 adds L2 eviction policies: the pre-filter is loaded evict_last, the bitmap probes and the
-// mask stores evict_first, so that streaming traffic does not push the filter out of L2.
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-
+// Loads of the membership tables are ld.global.nc.L1::no_allocate (no L1 line fill for a random probe). Measured and
+// dropped (profiles/): plain ld.global.nc / ld.global.cg, L2 eviction-priority hints on filter / table / mask traffic,
+// the persisting-L2 window, and .L2::64B on the table sectors (it halves the DRAM bytes, not the time: the ceiling is
+// L2-missing REQUESTS per second, profiles/r02_sector_fetch_microbench*).
 // word holding the membership bit of `kmer`, and the bit's index, for the k-mer that starts at a read
 // position whose low two bits are pos_lo2
 template <bool ANCH>
@@ -74,34 +61,17 @@ __device__ __forceinline__ void probe_slot(uint32_t kmer, unsigned pos_lo2, uint
     else { word = kmer >> 5; bit = kmer & 31u; }
 }
 
-template <int MODE>
-__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t word_index, unsigned long long pol_first) {
-    const uint32_t *p = bitmap + word_index;
-    if (MODE == 3) {
-        uint32_t v;
-        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_first));
-        return v;
-    }
-    if (MODE == 1) return __ldcg(p);
-    if (MODE == 2) {
-        uint32_t v;
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-        return v;
-    }
-    return __ldg(p);
+__device__ __forceinline__ uint32_t probe(const uint32_t *__restrict__ bitmap, uint32_t word_index) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(bitmap + word_index));
+    return v;
 }
 
-// Measured and dropped (profiles/r02_probe_variants3_wide_and_4bit_filters.jsonl): a dense-set variant with all eight table
-// sectors of a lane requested up front (80 registers, 3 blocks per SM): 81.2 ms against 80.0 ms. The dense probe already sits at
-// the rate at which HBM serves random sectors (profiles/r02_sector_fetch_microbench_table_sizes.jsonl), not at a latency limit.
 // (compiled for 5 / 6 blocks per SM the pair-keyed variant spills and runs in 94 / 115 ms against 86: profiles/r02_probe_variants5_blocks_per_sm.jsonl)
-template <int MODE, int FILT, bool ANCH>
+template <int FILT, bool ANCH>
 __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t *__restrict__ table = ANCH ? a.anchor : a.bitmap;
-    const unsigned long long pol_first = MODE == 3 ? l2_policy_evict_first() : 0ull;
-    const unsigned long long pol_last = MODE == 3 ? l2_policy_evict_last() : 0ull;
-    (void)pol_last;
     const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long n_tiles = a.tile_start[a.n];      // read on the device: no host round trip between the scan and the launch
@@ -125,7 +95,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     uint32_t k = __funnelshift_l(wb, wa, 2 * lane);
                     uint32_t word, bit;
                     probe_slot<ANCH>(k, lane & 3u, word, bit);         // tile_base is a multiple of 4
-                    hit = (probe<MODE>(table, word, pol_first) >> bit) & 1u;
+                    hit = (probe(table, word) >> bit) & 1u;
                 }
             }
             carry = __ballot_sync(0xffffffffu, hit) << 16;
@@ -153,9 +123,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         unsigned long long fb;
                         fl_filter_slot(fl_kmer_at(w, half * 16 + i), a.filter_log2_words, a.filter_kind, word, fb);
                         if (half * 16 + i < nvalid) {
-                            if (MODE == 3) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(f[i]) : "l"(a.filter + word), "l"(pol_last));
-                            else if (a.filter_kind & 2) f[i] = __ldcg(a.filter + word);   // L2 only (no L1 line fill)
-                            else f[i] = __ldg(a.filter + word);
+                            f[i] = __ldcg(a.filter + word);   // L2 only (no L1 line fill)
                         } else f[i] = 0ull;
                     }
                     go = 0;
@@ -209,16 +177,10 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                         const uint32_t key = (fl_kmer_at(w, p0 + 3) >> 6) & 0x3FFFFFFu;   // bases p0+3 .. p0+15
                         const bool need = p0 < nvalid && ((go >> (4 * g)) & 0xFu);
                         if (need) {
-                            if (MODE == 4)
-                                asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                             : "l"(table + (size_t)key * 8u));
-                            else
-                                asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                             : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
-                                               "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
-                                             : "l"(table + (size_t)key * 8u));
+                            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(sec[g][0]), "=r"(sec[g][1]), "=r"(sec[g][2]), "=r"(sec[g][3]), "=r"(sec[g][4]),
+                                           "=r"(sec[g][5]), "=r"(sec[g][6]), "=r"(sec[g][7])
+                                         : "l"(table + (size_t)key * 8u));
                         } else {
 #pragma unroll
                             for (int q = 0; q < 8; ++q) sec[g][q] = 0u;
@@ -241,7 +203,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
                     for (int i = 0; i < 16; ++i) {
                         const int p = half * 16 + i;
                         const uint32_t k = fl_kmer_at(w, p);
-                        words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe<MODE>(table, k >> 5, pol_first) : 0u;     // read.cpp:52
+                        words[i] = (p < nvalid && ((go >> i) & 1u)) ? probe(table, k >> 5) : 0u;     // read.cpp:52
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -260,8 +222,7 @@ __global__ void __launch_bounds__(256, 4) k_probe_paint(ProbeArgs a) {
             y |= y << 4;
             y |= y << 8;
             if (lb < padded) {
-                if (MODE == 3) asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" :: "l"(maskw + (lb >> 5)), "r"((uint32_t)(y >> 32)), "l"(pol_first));
-                else maskw[lb >> 5] = (uint32_t)(y >> 32);
+                maskw[lb >> 5] = (uint32_t)(y >> 32);
             }
             carry = __shfl_sync(0xffffffffu, h, 31);
         }
@@ -937,43 +898,18 @@ static int score_kmer_front(fl_ctx *ctx, const BatchView &b) {
         if (blocks < 1) blocks = 1;
         {
             KernelTimer kt(ctx, FL_KERNEL_PROBE_PAINT);
-            // keep the pre-filter resident in the L2 set-aside while the probe kernel streams reads past it
-            const bool persist = ctx->use_filter && ctx->l2_persist_bytes > 0;
-            if (persist) {
-                cudaStreamAttrValue attr{};
-                attr.accessPolicyWindow.base_ptr = ctx->d_filter;
-                size_t bytes = ((size_t)1 << ctx->filter_log2_words) * sizeof(unsigned long long);
-                attr.accessPolicyWindow.num_bytes = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
-                attr.accessPolicyWindow.hitRatio = bytes <= ctx->l2_persist_bytes ? 1.0f : (float)ctx->l2_persist_bytes / (float)bytes;
-                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
-            }
-            // Measured and dropped (profiles/r02_probe_filter_experiments.md): a minimizer-keyed pre-filter with per-lane load
-            // de-duplication (L1TEX 83 % -> 31 %, but 5x the false positives and the filter falls out of L2: 128 ms against
-            // 94 ms), L2 eviction hints and the persisting-L2 window on either flavour (+4..8 ms).
+            // Measured and dropped (profiles/r02_probe_filter_experiments.md, r02_probe_variants*.jsonl): a minimizer-keyed
+            // pre-filter with per-lane load de-duplication, L2 eviction hints, the persisting-L2 window, .L2::64B table loads.
             if (ctx->use_anchor) {
                 const int filt = !ctx->use_filter ? 0 : ((ctx->filter_kind & 4) ? 2 : ((ctx->filter_kind & 8) ? 3 : 1));
-                if (ctx->probe_mode == 4) {
-                    if (filt == 0) k_probe_paint<4, 0, true><<<blocks, 256, 0, st>>>(pa);
-                    else if (filt == 1) k_probe_paint<4, 1, true><<<blocks, 256, 0, st>>>(pa);
-                    else if (filt == 2) k_probe_paint<4, 2, true><<<blocks, 256, 0, st>>>(pa);
-                    else k_probe_paint<4, 3, true><<<blocks, 256, 0, st>>>(pa);
-                } else {
-                    if (filt == 0) k_probe_paint<2, 0, true><<<blocks, 256, 0, st>>>(pa);
-                    else if (filt == 1) k_probe_paint<2, 1, true><<<blocks, 256, 0, st>>>(pa);
-                    else if (filt == 2) k_probe_paint<2, 2, true><<<blocks, 256, 0, st>>>(pa);
-                    else k_probe_paint<2, 3, true><<<blocks, 256, 0, st>>>(pa);
-                }
+                if (filt == 0) k_probe_paint<0, true><<<blocks, 256, 0, st>>>(pa);
+                else if (filt == 1) k_probe_paint<1, true><<<blocks, 256, 0, st>>>(pa);
+                else if (filt == 2) k_probe_paint<2, true><<<blocks, 256, 0, st>>>(pa);
+                else k_probe_paint<3, true><<<blocks, 256, 0, st>>>(pa);
             } else if (ctx->use_filter) {                        // plain bitmap (FL_ANCHOR=0: cross-checks and profiling)
-                k_probe_paint<2, 1, false><<<blocks, 256, 0, st>>>(pa);
+                k_probe_paint<1, false><<<blocks, 256, 0, st>>>(pa);
             } else {
-                k_probe_paint<2, 0, false><<<blocks, 256, 0, st>>>(pa);
-            }
-            if (persist) {
-                cudaStreamAttrValue attr{};
-                attr.accessPolicyWindow.num_bytes = 0;
-                FL_CUDA(ctx, cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+                k_probe_paint<0, false><<<blocks, 256, 0, st>>>(pa);
             }
         }
         ctx->launches++;
