@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+#include "gzmem.h"
 #include "misc.h"
 #include "read.h"
 
@@ -55,22 +56,41 @@ struct StdoutGuard {
 struct MappedFile {
     const char *base = nullptr;
     uint64_t size = 0;
-    int fd = -1;
+    uint64_t map_bytes = 0;                                         // what munmap() gets
+    int fd = -1;                                                    // < 0: `base` is memory (an inflated gzip file), not a file mapping
+    bool gzip = false;                                              // the file on disk starts with the gzip magic
     bool open_plain(const std::string &path) {
         fd = ::open(path.c_str(), O_RDONLY);
         if (fd < 0) return false;
         struct stat st;
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 2) return false;
-        size = (uint64_t)st.st_size;
+        size = map_bytes = (uint64_t)st.st_size;
         void *p = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
         if (p == MAP_FAILED) return false;
         base = (const char *)p;
         madvise(p, (size_t)size, MADV_SEQUENTIAL);
         const unsigned char b0 = (unsigned char)base[0], b1 = (unsigned char)base[1];
-        return !(b0 == 0x1f && b1 == 0x8b);                    // gzip: the host reader inflates it
+        gzip = b0 == 0x1f && b1 == 0x8b;
+        return !gzip;
+    }
+    // gzip: inflate the whole file ONCE into memory (gzmem.h) and carry on as if it were a mapped plain file; the
+    // reference inflates it twice, once per pass (main.cpp:70-75, 263-269). false: leave it to the host reader.
+    bool inflate(std::string *why) {
+        if (!gzip || !base) return false;
+        InflatedInput in;
+        int threads = 0;
+        if (const char *e = getenv("FL_INFLATE_THREADS")) threads = atoi(e);
+        if (!inflate_gzip_memory((const unsigned char *)base, size, in, threads, 0, why)) return false;
+        munmap((void *)base, (size_t)map_bytes);
+        ::close(fd);
+        fd = -1;
+        size = in.size;
+        map_bytes = in.reserved;
+        base = in.take();
+        return true;
     }
     ~MappedFile() {
-        if (base) munmap((void *)base, (size_t)size);
+        if (base) munmap((void *)base, (size_t)map_bytes);
         if (fd >= 0) ::close(fd);
     }
 };
@@ -198,6 +218,10 @@ void run_shard(Shard &sh, const MappedFile &f, const std::vector<Chunk> &plan, i
                     uint64_t done = 0;
                     const uint64_t want = c.end - c.begin;
                     bool ok = true;
+                    if (f.fd < 0) {                                    // inflated gzip input: already in memory
+                        memcpy(ring.slot[k], f.base + c.begin, (size_t)want);
+                        done = want;
+                    }
                     while (done < want) {
                         const ssize_t r = pread(f.fd, ring.slot[k] + done, (size_t)(want - done), (off_t)(c.begin + done));
                         if (r <= 0) { ok = false; break; }
@@ -373,7 +397,11 @@ FeederOutcome run_text_feeder(Arguments &args, Kmers &kmers, const std::function
     FeederOutcome res;
     if (args.verbose || getenv("FL_HOST_PARSER")) return res;           // per-read dumps come from the host path
     MappedFile f;
-    if (!f.open_plain(args.input_reads)) return res;
+    if (!f.open_plain(args.input_reads)) {
+        std::string why;
+        if (!f.gzip || getenv("FL_GZ_HOST") || !f.inflate(&why)) return res;   // not gzip either, or declined (gzmem.h): the host reader
+        mark("gzip input inflated into memory");
+    }
     const int format = f.base[0] == '@' ? FL_TEXT_FASTQ : (f.base[0] == '>' ? FL_TEXT_FASTA : 0);
     if (!format) return res;
     const bool kmers_empty = kmers.empty();

@@ -11,8 +11,11 @@
 //   * with --gpus N the chunks are dealt to N contexts as contiguous ranges (one thread + one NCCL rank per
 //     GPU, the 16-mer set broadcast from GPU 0, fl_finalize collective): the output is what one GPU prints;
 //   * pass 2 writes the survivors with writev() straight from the mapping (no second parse, no copies).
-// Anything else -- gzip, CR LF, multi-line records, broken records, --verbose -- makes run_text_feeder return
-// handled == false before anything was printed to stdout, and main() runs the kseq-compatible host parser.
+//   * a gzip file is inflated ONCE into memory (gzmem.h: BGZF blocks by several host threads, anything else by one)
+//     and then goes down the same path; the reference inflates it once per pass.
+// Anything else -- CR LF, multi-line records, broken records, a gzip file that is damaged or would not fit in memory,
+// --verbose -- makes run_text_feeder return handled == false before anything was printed to stdout, and main() runs
+// the kseq-compatible host parser.
 #pragma once
 #include <functional>
 

@@ -193,6 +193,43 @@ def test_cli_duplicate_names_and_fallback_inputs(tmp_path):
         assert [l for l in err_o.splitlines() if l.startswith("Error")] == [l for l in err_r.splitlines() if l.startswith("Error")]
 
 
+def test_cli_gzip_input_is_inflated_once_and_parsed_on_the_device(tmp_path):
+    """.gz reads (the README's usual input): one member, concatenated members, BGZF blocks (inflated by several host
+    threads) all take the device-text path after ONE inflate into memory; a truncated file goes to the host reader,
+    whose messages are the reference's. stdout is the reference binary's, byte for byte, every time."""
+    import gzip
+    from tests.test_gzmem import bgzf
+    if not (os.path.exists(CLI) and orc.have_ref()):
+        pytest.skip("CLI or reference binary not built")
+    genome, reads = make_reads(31, n=300)
+    text = fastq_text(reads)
+    fa = util.write_fasta(tmp_path / "asm.fasta", [("c", genome)])
+    half = len(fastq_text(reads[:150]))
+    files = {
+        "one.fastq.gz": gzip.compress(text, 6),
+        "two.fastq.gz": gzip.compress(text[:half], 1) + gzip.compress(text[half:], 9),
+        "blocks.fastq.gz": bgzf(text, block=20000),
+    }
+    for name, data in files.items():
+        path = tmp_path / name
+        path.write_bytes(data)
+        for case in (["-p", "70", str(path)], ["-a", fa, "-p", "80", "--trim", "--split", "100", str(path)]):
+            rc_r, out_r, err_r = run([orc.REFCLI] + case)
+            rc_o, out_o, err_o = run([CLI] + case, {"FL_CLI_TIMING": "1", "FL_CHUNK_MB": "1", "FL_INFLATE_THREADS": "4"})
+            assert rc_o == rc_r == 0, err_o[-2000:]
+            assert "gzip input inflated" in err_o and "device parse" in err_o, err_o[-2000:]
+            assert out_o == out_r and len(out_r) > 0
+            rc_h, out_h, _ = run([CLI] + case, {"FL_GZ_HOST": "1"})            # the streaming host reader, for comparison
+            assert rc_h == 0 and out_h == out_r
+    broken = tmp_path / "truncated.fastq.gz"
+    broken.write_bytes(files["one.fastq.gz"][:len(files["one.fastq.gz"]) // 2])
+    rc_r, out_r, err_r = run([orc.REFCLI, "-p", "70", str(broken)])
+    rc_o, out_o, err_o = run([CLI, "-p", "70", str(broken)], {"FL_CLI_TIMING": "1"})
+    assert "gzip input inflated" not in err_o
+    assert (rc_o, out_o) == (rc_r, out_r)
+    assert [l for l in err_o.splitlines() if l.startswith("Error")] == [l for l in err_r.splitlines() if l.startswith("Error")]
+
+
 def test_cli_sharded_over_gpus_prints_what_one_gpu_prints(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
