@@ -205,6 +205,14 @@ class Context:
         out.update(status="fallback" if st.value else "ok", n=n.value, consumed=used.value)
         return out
 
+    def kmers_add_text(self, data: bytes, fastq=True, is_last=True, multiple_copies=False):
+        """fl_kmers_add_text on one chunk of a reference file (FASTQ / FASTA text)."""
+        n, nb, used, st = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        self._ck(self.L.fl_kmers_add_text(self.h, capi.ptr(buf), len(data), 1 if fastq else 2, int(is_last), int(multiple_copies),
+                                          C.byref(n), C.byref(nb), C.byref(used), C.byref(st)), "fl_kmers_add_text")
+        return dict(status="fallback" if st.value else "ok", n=n.value, bases=nb.value, consumed=used.value)
+
     def push_device(self, batch):
         self._ck(self.L.fl_reads_push_device(self.h, C.byref(batch)), "fl_reads_push_device")
 

@@ -134,6 +134,8 @@ SYMBOLS = [
     ("fl_reads_push", C.c_int, [_P, C.POINTER(Batch)]),
     ("fl_reads_push_text", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.POINTER(TextRecords), C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    ("fl_kmers_add_text", C.c_int, [_P, _P, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     ("fl_host_alloc", C.c_int, [C.c_uint64, C.POINTER(_P)]),
     ("fl_host_free", None, [_P]),
     ("fl_host_register", C.c_int, [_P, C.c_uint64]),

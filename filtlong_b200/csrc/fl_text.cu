@@ -152,7 +152,7 @@ template <bool PHRED>
 __global__ void __launch_bounds__(256) k_text_gather(const uint8_t *__restrict__ text, unsigned long long n_bytes, uint32_t n_rec,
                                                      const uint32_t *__restrict__ src_off, const int32_t *__restrict__ len,
                                                      const unsigned long long *__restrict__ off, uint32_t *__restrict__ seq2b,
-                                                     uint8_t *__restrict__ qual) {
+                                                     uint8_t *__restrict__ qual, uint32_t *__restrict__ nmask) {
     const unsigned lane = threadIdx.x & 31;
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const uint32_t *t32 = reinterpret_cast<const uint32_t *>(text);
@@ -169,12 +169,13 @@ __global__ void __launch_bounds__(256) k_text_gather(const uint8_t *__restrict__
                 dst[0] = make_uint4(c[0], c[1], c[2], c[3]);
                 dst[1] = make_uint4(c[4], c[5], c[6], c[7]);
             } else {
-                uint32_t w[2] = {0u, 0u};
+                uint32_t w[2] = {0u, 0u}, m = 0u;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     uint32_t code8, other4;
                     fl_pack4(c[i], code8, other4);
                     w[i >> 2] |= code8 << (24 - 8 * (i & 3));
+                    m |= other4 << (4 * i);                              // non-ACGT characters (reference sequences: kmers.cpp:199-219)
                 }
                 // bases at or beyond L must be code 0 for nobody in particular (no kernel forms a 16-mer there), but a
                 // clean tail keeps batches comparable with the host packer's
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(256) k_text_gather(const uint8_t *__restrict__
                     else if (nv < 32) { if (nv > 16) w[1] &= ~(0xFFFFFFFFu >> (2 * (nv - 16))); else w[1] = 0; }
                 }
                 reinterpret_cast<uint2 *>(seq2b + ((dof + b) >> 4))[0] = make_uint2(w[0], w[1]);
+                if (nmask) nmask[(dof + b) >> 5] = nv >= 32 ? m : (nv <= 0 ? 0u : m & ((1u << nv) - 1u));
             }
         }
     }
@@ -195,15 +197,109 @@ __global__ void k_text_u32_to_u64(const uint32_t *__restrict__ in, uint32_t n, u
     if (i < n) out[i] = base + in[i];
 }
 
-__global__ void k_text_sum_len(const int32_t *len, uint32_t n, unsigned long long *out) {
+__global__ void k_text_sum_len(const int32_t *len, uint32_t n, unsigned long long *out, int min_len = 0) {
     unsigned long long s = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += (unsigned long long)len[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (len[i] >= min_len) s += (unsigned long long)len[i];
 #pragma unroll
     for (int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
 }  // namespace
+
+// The front half of both text entry points: stage the chunk, index its newlines, validate the records of the common
+// layout and lay out the arena (padded offsets). ix.done: the caller returns at once (nothing to do, or not the layout).
+struct TextIndex {
+    fl_ctx::Staging *S = nullptr;
+    RecArgs ra{};
+    const uint8_t *text = nullptr;
+    unsigned long long n_rec = 0, padded_bases = 0, consumed = 0;
+    bool done = false;
+};
+
+static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lpr, int is_last_chunk, bool have_cap, uint64_t cap,
+                      uint64_t *n_records, int *status, TextIndex &ix) {
+    // ---- stage the text: copy stream, double buffered like fl_reads_push ----
+    const int slot = c->stg_next;
+    c->stg_next ^= 1;
+    fl_ctx::Staging &S = c->stg[slot];
+    ix.S = &S;
+    if (!S.consumed) FL_CUDA(c, cudaEventCreateWithFlags(&S.consumed, cudaEventDisableTiming));
+    if (S.in_use) FL_CUDA(c, cudaEventSynchronize(S.consumed));
+    S.in_use = false;
+    cudaStream_t st = c->stream;
+    FL_CUDA(c, S.ascii.reserve((size_t)n_bytes + 64, 0, c->copy_stream));
+    FL_CUDA(c, cudaMemcpyAsync(S.ascii.p, host_text, (size_t)n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
+    FL_CUDA(c, cudaStreamWaitEvent(st, c->ev_copied, 0));
+    const uint8_t *text = S.ascii.p;
+    ix.text = text;
+    // ---- newline index ----
+    const unsigned long long n_blocks = (n_bytes + TX_LINES_PER_WARP - 1) / TX_LINES_PER_WARP;
+    FL_CUDA(c, c->sc_u64a.reserve(n_blocks + 1, 0, st));
+    unsigned grid = fl_blocks(n_blocks * 32, 256);
+    if (grid > (unsigned)c->sm_count * 16) grid = (unsigned)c->sm_count * 16;
+    k_text_count<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p);
+    c->launches++;
+    FL_TRY(fl_exclusive_scan_u64(c, c->sc_u64a.p, c->sc_u64a.p, n_blocks, c->d_scalars));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 1, text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaStreamSynchronize(st));
+    unsigned long long n_lines = c->h_scalars[0];
+    const bool ends_with_nl = (reinterpret_cast<const unsigned char *>(c->h_scalars + 1))[0] == '\n';
+    unsigned long long n_lines_virtual = n_lines + ((is_last_chunk && !ends_with_nl) ? 1 : 0);   // the file's last line may lack its newline
+    const unsigned long long n_rec = n_lines_virtual / lpr;
+    ix.n_rec = n_rec;
+    if (n_rec == 0 || n_rec > 0xFFFFFFF0ull) {
+        // not even one whole record in the chunk (or an absurd count): let the host parser deal with this input
+        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        *status = is_last_chunk && n_lines_virtual == 0 ? FL_TEXT_OK : FL_TEXT_FALLBACK;
+        ix.done = true;
+        return FL_OK;
+    }
+    if (have_cap && cap < n_rec) {                          // nothing was done: *n_records tells the caller what to provide
+        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        *n_records = n_rec;
+        c->set_error("fl_reads_push_text: the record arrays are too small");
+        return FL_ERANGE;
+    }
+    FL_CUDA(c, c->tx_nl.reserve(n_lines + 1, 0, st));
+    k_text_positions<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p, c->tx_nl.p);
+    c->launches++;
+    // ---- records ----
+    const size_t n = (size_t)n_rec;
+    FL_CUDA(c, c->tx_u32.reserve(5 * n + 8, 0, st));
+    FL_CUDA(c, c->sc_u64b.reserve(n + 1, 0, st));       // name hashes
+    FL_CUDA(c, S.off.reserve(n + 1, 0, st));            // padded lengths -> offsets
+    FL_CUDA(c, S.len.reserve(n, 0, st));
+    RecArgs &ra = ix.ra;
+    ra = RecArgs{};
+    ra.text = text; ra.n_bytes = n_bytes; ra.nl = c->tx_nl.p; ra.n_lines = n_lines; ra.n_rec = (uint32_t)n_rec; ra.lines_per_rec = lpr;
+    ra.name_off = c->tx_u32.p; ra.name_len = c->tx_u32.p + n; ra.comment_len = c->tx_u32.p + 2 * n; ra.seq_off = c->tx_u32.p + 3 * n;
+    ra.qual_off = c->tx_u32.p + 4 * n;
+    ra.len = S.len.p; ra.name_hash = c->sc_u64b.p; ra.padded = reinterpret_cast<unsigned long long *>(S.off.p);
+    int *d_bad = reinterpret_cast<int *>(c->d_scalars + 27);
+    FL_CUDA(c, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
+    ra.bad = d_bad;
+    k_text_records<<<fl_blocks(n, 256), 256, 0, st>>>(ra);
+    c->launches++;
+    FL_TRY(fl_exclusive_scan_u64(c, reinterpret_cast<unsigned long long *>(S.off.p), reinterpret_cast<unsigned long long *>(S.off.p), n, c->d_scalars + 1));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 2, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 3, c->d_scalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 4, c->tx_nl.p + (n_rec * lpr - 1 < n_lines ? n_rec * lpr - 1 : n_lines - 1), sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaStreamSynchronize(st));
+    if (c->h_scalars[2] != 0) {                             // not the simple layout: nothing was done
+        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        *status = FL_TEXT_FALLBACK;
+        ix.done = true;
+        return FL_OK;
+    }
+    ix.padded_bases = c->h_scalars[3];
+    ix.consumed = (n_rec * lpr - 1 < n_lines) ? (unsigned long long)(*reinterpret_cast<uint32_t *>(c->h_scalars + 4)) + 1 : n_bytes;
+    return FL_OK;
+}
 
 extern "C" int fl_reads_push_text(fl_ctx *c, const char *host_text, uint64_t n_bytes, int format, int is_last_chunk,
                                   const fl_text_records *out, uint64_t *n_records, uint64_t *bytes_consumed, int *status) {
@@ -221,78 +317,15 @@ extern "C" int fl_reads_push_text(fl_ctx *c, const char *host_text, uint64_t n_b
     const bool kmer_mode = c->n_kmers > 0;
     if (!kmer_mode && format == FL_TEXT_FASTA) { *status = FL_TEXT_FALLBACK; return FL_OK; }    // main.cpp:103-106 is the host's error to print
     const int lpr = format == FL_TEXT_FASTQ ? 4 : 2;
-    // ---- stage the text: copy stream, double buffered like fl_reads_push ----
-    const int slot = c->stg_next;
-    c->stg_next ^= 1;
-    fl_ctx::Staging &S = c->stg[slot];
-    if (!S.consumed) FL_CUDA(c, cudaEventCreateWithFlags(&S.consumed, cudaEventDisableTiming));
-    if (S.in_use) FL_CUDA(c, cudaEventSynchronize(S.consumed));
-    S.in_use = false;
+    TextIndex ix;
+    FL_TRY(text_index(c, host_text, n_bytes, lpr, is_last_chunk, out != nullptr, out ? out->cap : 0, n_records, status, ix));
+    if (ix.done) return FL_OK;
+    fl_ctx::Staging &S = *ix.S;
     cudaStream_t st = c->stream;
-    FL_CUDA(c, S.ascii.reserve((size_t)n_bytes + 64, 0, c->copy_stream));
-    FL_CUDA(c, cudaMemcpyAsync(S.ascii.p, host_text, (size_t)n_bytes, cudaMemcpyHostToDevice, c->copy_stream));
-    FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
-    FL_CUDA(c, cudaStreamWaitEvent(st, c->ev_copied, 0));
-    const uint8_t *text = S.ascii.p;
-    // ---- newline index ----
-    const unsigned long long n_blocks = (n_bytes + TX_LINES_PER_WARP - 1) / TX_LINES_PER_WARP;
-    FL_CUDA(c, c->sc_u64a.reserve(n_blocks + 1, 0, st));
-    unsigned grid = fl_blocks(n_blocks * 32, 256);
-    if (grid > (unsigned)c->sm_count * 16) grid = (unsigned)c->sm_count * 16;
-    k_text_count<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p);
-    c->launches++;
-    FL_TRY(fl_exclusive_scan_u64(c, c->sc_u64a.p, c->sc_u64a.p, n_blocks, c->d_scalars));
-    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 1, text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
-    FL_CUDA(c, cudaStreamSynchronize(st));
-    unsigned long long n_lines = c->h_scalars[0];
-    const bool ends_with_nl = (reinterpret_cast<const unsigned char *>(c->h_scalars + 1))[0] == '\n';
-    unsigned long long n_lines_virtual = n_lines + ((is_last_chunk && !ends_with_nl) ? 1 : 0);   // the file's last line may lack its newline
-    const unsigned long long n_rec = n_lines_virtual / lpr;
-    if (n_rec == 0 || n_rec > 0xFFFFFFF0ull) {
-        // not even one whole record in the chunk (or an absurd count): let the host parser deal with this input
-        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-        *status = is_last_chunk && n_lines_virtual == 0 ? FL_TEXT_OK : FL_TEXT_FALLBACK;
-        return FL_OK;
-    }
-    if (out && out->cap < n_rec) {                          // nothing was scored: *n_records tells the caller what to provide
-        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-        *n_records = n_rec;
-        c->set_error("fl_reads_push_text: the record arrays are too small");
-        return FL_ERANGE;
-    }
-    FL_CUDA(c, c->tx_nl.reserve(n_lines + 1, 0, st));
-    k_text_positions<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p, c->tx_nl.p);
-    c->launches++;
-    // ---- records ----
+    const uint8_t *text = ix.text;
+    const unsigned long long n_rec = ix.n_rec, padded_bases = ix.padded_bases, consumed = ix.consumed;
     const size_t n = (size_t)n_rec;
-    FL_CUDA(c, c->tx_u32.reserve(5 * n + 8, 0, st));
-    FL_CUDA(c, c->sc_u64b.reserve(n + 1, 0, st));       // name hashes
-    FL_CUDA(c, S.off.reserve(n + 1, 0, st));            // padded lengths -> offsets
-    FL_CUDA(c, S.len.reserve(n, 0, st));
-    RecArgs ra{};
-    ra.text = text; ra.n_bytes = n_bytes; ra.nl = c->tx_nl.p; ra.n_lines = n_lines; ra.n_rec = (uint32_t)n_rec; ra.lines_per_rec = lpr;
-    ra.name_off = c->tx_u32.p; ra.name_len = c->tx_u32.p + n; ra.comment_len = c->tx_u32.p + 2 * n; ra.seq_off = c->tx_u32.p + 3 * n;
-    ra.qual_off = c->tx_u32.p + 4 * n;
-    ra.len = S.len.p; ra.name_hash = c->sc_u64b.p; ra.padded = reinterpret_cast<unsigned long long *>(S.off.p);
-    int *d_bad = reinterpret_cast<int *>(c->d_scalars + 27);
-    FL_CUDA(c, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
-    ra.bad = d_bad;
-    k_text_records<<<fl_blocks(n, 256), 256, 0, st>>>(ra);
-    c->launches++;
-    FL_TRY(fl_exclusive_scan_u64(c, reinterpret_cast<unsigned long long *>(S.off.p), reinterpret_cast<unsigned long long *>(S.off.p), n, c->d_scalars + 1));
-    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 2, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 3, c->d_scalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 4, c->tx_nl.p + (n_rec * lpr - 1 < n_lines ? n_rec * lpr - 1 : n_lines - 1), sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, st));
-    FL_CUDA(c, cudaStreamSynchronize(st));
-    if (c->h_scalars[2] != 0) {                             // not the simple layout: nothing was scored
-        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-        *status = FL_TEXT_FALLBACK;
-        return FL_OK;
-    }
-    const unsigned long long padded_bases = c->h_scalars[3];
-    const unsigned long long consumed = (n_rec * lpr - 1 < n_lines) ? (unsigned long long)(*reinterpret_cast<uint32_t *>(c->h_scalars + 4)) + 1 : n_bytes;
+    RecArgs &ra = ix.ra;
     // ---- gather into the arena, score ----
     BatchView v{};
     v.n = (uint32_t)n_rec; v.padded_bases = padded_bases; v.off = S.off.p; v.len = S.len.p;
@@ -301,12 +334,12 @@ extern "C" int fl_reads_push_text(fl_ctx *c, const char *host_text, uint64_t n_b
     if (kmer_mode) {
         FL_CUDA(c, S.seq.reserve((size_t)(padded_bases >> 4) + 8, 0, st));
         k_text_gather<false><<<ggrid, 256, 0, st>>>(text, n_bytes, (uint32_t)n_rec, ra.seq_off, S.len.p, reinterpret_cast<unsigned long long *>(S.off.p),
-                                                    S.seq.p, nullptr);
+                                                    S.seq.p, nullptr, nullptr);
         v.seq2b = S.seq.p;
     } else {
         FL_CUDA(c, S.qual.reserve((size_t)padded_bases + 64, 0, st));
         k_text_gather<true><<<ggrid, 256, 0, st>>>(text, n_bytes, (uint32_t)n_rec, ra.qual_off, S.len.p, reinterpret_cast<unsigned long long *>(S.off.p),
-                                                   nullptr, S.qual.p);
+                                                   nullptr, S.qual.p, nullptr);
         v.qual = S.qual.p;
     }
     c->launches++;
@@ -343,6 +376,58 @@ extern "C" int fl_reads_push_text(fl_ctx *c, const char *host_text, uint64_t n_b
     FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the caller may reuse its buffer now
     *n_records = n_rec;
     *bytes_consumed = consumed;
+    return FL_OK;
+}
+
+// The reference set from TEXT (kmers.cpp:75-134 behind kseq): the same front half, then the sequences -- every record's,
+// also those shorter than 16, which add nothing (kmers.cpp:99-100) but are counted (kmers.cpp:96) -- packed with their
+// non-ACGT mask and handed to the build kernels.
+extern "C" int fl_kmers_add_text(fl_ctx *c, const char *host_text, uint64_t n_bytes, int format, int is_last_chunk, int require_multiple_copies,
+                                 uint64_t *n_records, uint64_t *n_bases, uint64_t *bytes_consumed, int *status) {
+    FL_ENTER(c);
+    if (!host_text || !n_records || !n_bases || !bytes_consumed || !status || (format != FL_TEXT_FASTQ && format != FL_TEXT_FASTA)) {
+        c->set_error("fl_kmers_add_text: bad arguments");
+        return FL_EINVAL;
+    }
+    if (n_bytes >= ((uint64_t)1 << 31)) { c->set_error("fl_kmers_add_text: a chunk must be smaller than 2 GiB"); return FL_ERANGE; }
+    *n_records = 0;
+    *n_bases = 0;
+    *bytes_consumed = 0;
+    *status = FL_TEXT_OK;
+    if (n_bytes == 0) return FL_OK;
+    const int lpr = format == FL_TEXT_FASTQ ? 4 : 2;
+    TextIndex ix;
+    FL_TRY(text_index(c, host_text, n_bytes, lpr, is_last_chunk, false, 0, n_records, status, ix));
+    if (ix.done) return FL_OK;
+    fl_ctx::Staging &S = *ix.S;
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t)ix.n_rec;
+    BatchView v{};
+    v.n = (uint32_t)ix.n_rec; v.padded_bases = ix.padded_bases; v.off = S.off.p; v.len = S.len.p;
+    unsigned ggrid = fl_blocks(n * 32, 256);
+    if (ggrid > (unsigned)c->sm_count * 16) ggrid = (unsigned)c->sm_count * 16;
+    FL_CUDA(c, S.seq.reserve((size_t)(ix.padded_bases >> 4) + 8, 0, st));
+    FL_CUDA(c, S.nmask.reserve((size_t)(ix.padded_bases >> 5) + 8, 0, st));
+    k_text_gather<false><<<ggrid, 256, 0, st>>>(ix.text, n_bytes, (uint32_t)ix.n_rec, ix.ra.seq_off, S.len.p,
+                                                reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, nullptr, S.nmask.p);
+    c->launches++;
+    v.seq2b = S.seq.p;
+    v.nmask = S.nmask.p;
+    // bases of the sequences that take part (the progress line of kmers.cpp:101,123-126 counts only those)
+    unsigned long long *d_sum = c->d_scalars + 28;
+    FL_CUDA(c, cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), st));
+    k_text_sum_len<<<c->sm_count, 256, 0, st>>>(S.len.p, (uint32_t)ix.n_rec, d_sum, 16);
+    c->launches++;
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 5, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaGetLastError());
+    FL_TRY(fl_kmers_add_view(c, v, require_multiple_copies ? 1 : 0));       // synchronises the stream on its way
+    FL_CUDA(c, cudaEventRecord(S.consumed, st));
+    S.in_use = true;
+    FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));   // the caller may reuse its buffer now
+    FL_CUDA(c, cudaStreamSynchronize(st));
+    *n_records = ix.n_rec;
+    *n_bases = c->h_scalars[5];
+    *bytes_consumed = ix.consumed;
     return FL_OK;
 }
 

@@ -6,6 +6,17 @@
 
 FastxReader::FastxReader(const std::string &path) : buf_(new unsigned char[kBuf]) { fp_ = gzopen(path.c_str(), "r"); }
 
+FastxReader::FastxReader(const char *mem, uint64_t n_bytes) : mem_(mem), mem_n_(n_bytes), buf_(new unsigned char[kBuf]) {}
+
+int FastxReader::refill() {
+    if (!mem_) return gzread(fp_, buf_, kBuf);
+    const uint64_t left = mem_n_ - mem_pos_;
+    const int n = left < (uint64_t)kBuf ? (int)left : kBuf;
+    memcpy(buf_, mem_ + mem_pos_, (size_t)n);
+    mem_pos_ += (uint64_t)n;
+    return n;
+}
+
 FastxReader::~FastxReader() {
     if (fp_) gzclose(fp_);
     delete[] buf_;
@@ -17,7 +28,7 @@ int FastxReader::getc() {
     if (begin_ >= end_) {
         buf_base_ += (uint64_t)end_;
         begin_ = 0;
-        end_ = gzread(fp_, buf_, kBuf);
+        end_ = refill();
         if (end_ == 0) { eof_ = true; return -1; }
         if (end_ < 0) { eof_ = true; err_ = true; end_ = 0; return -3; }
     }
@@ -33,7 +44,7 @@ bool FastxReader::get_line(std::string &s, bool append) {
             if (eof_) break;
             buf_base_ += (uint64_t)end_;
             begin_ = 0;
-            end_ = gzread(fp_, buf_, kBuf);
+            end_ = refill();
             if (end_ == 0) { eof_ = true; break; }
             if (end_ < 0) { eof_ = true; err_ = true; end_ = 0; return false; }
         }

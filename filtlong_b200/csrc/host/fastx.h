@@ -20,8 +20,11 @@
 class FastxReader {
 public:
     explicit FastxReader(const std::string &path);
+    // the same parser over bytes already in memory (a mapped plain file or an inflated gzip file, from any record
+    // boundary on): what a device-text caller falls back to in the middle of a file
+    FastxReader(const char *mem, uint64_t n_bytes);
     ~FastxReader();
-    bool ok() const { return fp_ != nullptr; }
+    bool ok() const { return fp_ != nullptr || mem_ != nullptr; }
     int64_t next();
     std::string name, comment, seq, qual;
     bool is_fastq = false;
@@ -41,7 +44,10 @@ private:
     // appends the rest of the current line to s (without the newline); returns false at EOF with
     // nothing read
     bool get_line(std::string &s, bool append);
+    int refill();                      // the next bytes of the stream into buf_: > 0 bytes, 0 at the end, < 0 on a stream error
     gzFile fp_ = nullptr;
+    const char *mem_ = nullptr;
+    uint64_t mem_n_ = 0, mem_pos_ = 0;
     static constexpr int kBuf = 1 << 16;
     unsigned char *buf_;
     int begin_ = 0, end_ = 0;

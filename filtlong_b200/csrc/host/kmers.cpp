@@ -1,12 +1,15 @@
 // filtlong_b200/csrc/host/kmers.cpp -- see kmers.h. Log lines follow reference src/kmers.cpp:50-72.
 #include "kmers.h"
 
+#include <stdlib.h>
+
 #include <iostream>
 #include <stdexcept>
 
 #include "arena.h"
 #include "fastx.h"
 #include "misc.h"
+#include "textsrc.h"
 
 void Kmers::check(fl_ctx *ctx, int rc, const char *what) {
     if (rc == FL_OK) return;
@@ -58,32 +61,76 @@ void Kmers::add_assembly_fasta(std::string filename) {
               << int_to_string((long long)size()) << " 16-mers\n\n";
 }
 
+// The reference's loop (kmers.cpp:75-134) parses one record at a time through kseq on the calling thread. Here the file
+// is one byte range (mapped, or a gzip file inflated once: textsrc.h) whose record-aligned chunks go to the device as
+// TEXT (fl_kmers_add_text): records, validation, 2-bit packing and the non-ACGT mask all happen there. The first chunk
+// that is not in the common layout (wrapped FASTA, CR LF, a broken record ...) -- and everything after it -- is parsed
+// by the kseq-compatible host reader from that chunk's first byte, so the adds stay in file order and the reader stops
+// where the reference's would (a parse error silently ends hashing: kmers.cpp:90-94).
 int Kmers::add_reference(const std::string &filename, bool multi) {
-    const uint64_t kBatchBases = 256ull << 20;
-    HostArena arena(true, false, true);
-    FastxReader in(filename);
     int sequence_count = 0;
     long long base_count = 0, last_progress = 0;
-    auto flush = [&]() {
-        if (arena.empty()) return;
-        fl_batch b = arena.batch();
-        fl_ctx *c = context();
-        check(c, fl_kmers_add_batch(c, &b, multi ? 1 : 0), "fl_kmers_add_batch");
-        arena.clear();
-    };
-    while (in.ok() && in.next() >= 0) {           // a parse error silently ends hashing (kmers.cpp:90-94)
-        ++sequence_count;
-        if (in.seq.size() < 16) continue;          // kmers.cpp:99-100
-        base_count += (long long)in.seq.size();
-        arena.add(in.seq.data(), nullptr, (int64_t)in.seq.size());
-        if (arena.padded_bases() >= kBatchBases) flush();
-        if (base_count - last_progress >= 483611) {    // the reference's progress cadence (kmers.cpp:123-126)
+    auto progress = [&](bool force) {
+        if (force || base_count - last_progress >= 483611) {           // the reference's progress cadence (kmers.cpp:123-126)
             last_progress = base_count;
             print_hash_progress(filename, base_count);
         }
+    };
+    // the host parser over `in`, feeding packed batches (fl_kmers_add_batch)
+    auto host_parse = [&](FastxReader &in) {
+        const uint64_t kBatchBases = 256ull << 20;
+        HostArena arena(true, false, true);
+        auto flush = [&]() {
+            if (arena.empty()) return;
+            fl_batch b = arena.batch();
+            fl_ctx *c = context();
+            check(c, fl_kmers_add_batch(c, &b, multi ? 1 : 0), "fl_kmers_add_batch");
+            arena.clear();
+        };
+        while (in.ok() && in.next() >= 0) {        // a parse error silently ends hashing (kmers.cpp:90-94)
+            ++sequence_count;
+            if (in.seq.size() < 16) continue;      // kmers.cpp:99-100
+            base_count += (long long)in.seq.size();
+            arena.add(in.seq.data(), nullptr, (int64_t)in.seq.size());
+            if (arena.padded_bases() >= kBatchBases) flush();
+            progress(false);
+        }
+        flush();
+    };
+    MappedFile f;
+    std::vector<Chunk> plan;
+    const bool timing = getenv("FL_CLI_TIMING") != nullptr;
+    uint64_t target = 128ull << 20;
+    if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
+    if (target < (1ull << 20)) target = 1ull << 20;
+    if (target > (1024ull << 20)) target = 1024ull << 20;
+    bool text_path = !getenv("FL_HOST_PARSER") && f.open_any(filename) && f.format() != 0 &&
+                     plan_chunks(f.base, f.size, f.format(), target, target, plan) && !plan.empty();
+    if (text_path) {
+        fl_ctx *c = context();
+        for (size_t i = 0; i < plan.size(); ++i) {
+            const Chunk &ch = plan[i];
+            uint64_t n_rec = 0, n_bases = 0, used = 0;
+            int status = FL_TEXT_OK;
+            check(c, fl_kmers_add_text(c, f.base + ch.begin, ch.end - ch.begin, f.format(), i + 1 == plan.size() ? 1 : 0, multi ? 1 : 0,
+                                       &n_rec, &n_bases, &used, &status), "fl_kmers_add_text");
+            if (status != FL_TEXT_OK || used != ch.end - ch.begin) {    // nothing of this chunk was added: the host reader takes over here
+                if (timing) std::cerr << "[timing] reference " << filename << ": host reader from byte " << ch.begin << "\n";
+                FastxReader in(f.base + ch.begin, f.size - ch.begin);
+                host_parse(in);
+                break;
+            }
+            sequence_count += (int)n_rec;
+            base_count += (long long)n_bases;
+            progress(false);
+            if (timing && i + 1 == plan.size()) std::cerr << "[timing] reference " << filename << ": device text, " << plan.size() << " chunks\n";
+        }
+    } else {
+        if (timing) std::cerr << "[timing] reference " << filename << ": host reader\n";
+        FastxReader in(filename);
+        host_parse(in);
     }
-    flush();
-    print_hash_progress(filename, base_count);
+    progress(true);
     std::cerr << "\n";
     return sequence_count;
 }

@@ -122,6 +122,59 @@ def test_push_text_fasta_and_fallbacks():
     ctx.close()
 
 
+@pytest.mark.parametrize("multi", [False, True])
+def test_kmers_add_text_builds_the_set_the_packed_path_builds(multi):
+    """fl_kmers_add_text (the reference file as text: kmers.cpp:75-134 behind kseq) against fl_kmers_add_batch on the
+    same sequences: identical 16-mer sets, one copy and >= 4 copies, with N runs, lower case, sequences shorter than
+    16 (counted, adding nothing), chunked at record boundaries; and against the oracle's set."""
+    rng = np.random.default_rng(41 + multi)
+    genome = bytearray(util.rand_seq(rng, 30000))
+    genome[5000:5040] = b"N" * 40
+    genome[12000:12100] = bytes(genome[12000:12100]).lower()
+    genome = bytes(genome)
+    if multi:       # short reads, deep enough that many 16-mers are seen four times
+        seqs = [genome[s:s + 150] for s in rng.integers(0, len(genome) - 150, size=3000)]
+        seqs[7] = b"ACGTNACGT"                                        # < 16: counted, contributes nothing
+        seqs[11] = b"acgtacgtacgtacgtacgtnnnnacgtacgtacgtacgtacgtacgtac"
+        recs = [(b"r%d" % i, q, b"I" * len(q)) for i, q in enumerate(seqs)]
+        text = fastq_text(recs)
+    else:           # "contigs", unwrapped FASTA
+        seqs = [genome[:9000], genome[9000:9010], genome[9010:30000], b"ACGTACGTACGTACGT", b"TTTTTTTTTTTTTTT"]
+        text = b"".join(b">contig_%d some words\n" % i + q + b"\n" for i, q in enumerate(seqs))
+    a, b = api.Context(api.make_params()), api.Context(api.make_params())
+    b.kmers_add(seqs, multi)
+    # three record-aligned chunks
+    lines = text.split(b"\n")[:-1]
+    lpr = 4 if multi else 2
+    n_rec = len(lines) // lpr
+    cuts = [0, n_rec // 3, 2 * n_rec // 3, n_rec]
+    total_rec = total_bases = 0
+    for i in range(3):
+        piece = b"".join(l + b"\n" for l in lines[cuts[i] * lpr:cuts[i + 1] * lpr])
+        if not piece:
+            continue
+        r = a.kmers_add_text(piece, fastq=multi, is_last=(i == 2), multiple_copies=multi)
+        assert r["status"] == "ok" and r["consumed"] == len(piece), r
+        total_rec += r["n"]
+        total_bases += r["bases"]
+    assert total_rec == len(seqs)
+    assert total_bases == sum(len(q) for q in seqs if len(q) >= 16)
+    assert a.kmers_count() == b.kmers_count() > 0
+    assert np.array_equal(a.kmers_export(), b.kmers_export())
+    ok = orc.Kmers()
+    (ok.add_short_reads if multi else ok.add_assembly)(seqs)
+    assert np.array_equal(a.kmers_export(), np.sort(ok.dump()))
+    # not the common layout: nothing is added, the caller parses on the host
+    before = a.kmers_count()
+    wrapped = b">c\nACGTACGTACGTACGTACGT\nACGTACGTACGTACGTACGT\n"
+    crlf = b">c\r\nACGTACGTACGTACGTACGTACGT\r\n"
+    for bad in (wrapped, crlf, b"@r\nACGTACGTACGTACGTAAAA\n+\nIIII\n"):
+        r = a.kmers_add_text(bad, fastq=bad.startswith(b"@"), is_last=True, multiple_copies=multi)
+        assert r["status"] == "fallback" and r["n"] == 0
+    assert a.kmers_count() == before
+    a.close(); b.close()
+
+
 def run(cmd, env=None):
     e = dict(os.environ, LC_ALL="C")
     e.pop("LANG", None)
@@ -228,6 +281,48 @@ def test_cli_gzip_input_is_inflated_once_and_parsed_on_the_device(tmp_path):
     assert "gzip input inflated" not in err_o
     assert (rc_o, out_o) == (rc_r, out_r)
     assert [l for l in err_o.splitlines() if l.startswith("Error")] == [l for l in err_r.splitlines() if l.startswith("Error")]
+
+
+def test_cli_reference_files_take_the_device_text_path(tmp_path):
+    """-a with an unwrapped FASTA and -1/-2 with plain and gzip FASTQ files go to the device as text (Kmers::add_reference
+    -> fl_kmers_add_text); a wrapped FASTA and a file that turns multi-line half way go (from there on) through the
+    host reader. Same stdout and the same log lines as the reference binary every time."""
+    import gzip
+    if not (os.path.exists(CLI) and orc.have_ref()):
+        pytest.skip("CLI or reference binary not built")
+    genome, reads = make_reads(51, n=200)
+    fq = tmp_path / "reads.fastq"
+    fq.write_bytes(fastq_text(reads))
+    contigs = [(b"c1 first", genome[:20000]), (b"c2", genome[20000:20010]), (b"c3", genome[20010:])]
+    flat = tmp_path / "flat.fasta"
+    flat.write_bytes(b"".join(b">" + n + b"\n" + q + b"\n" for n, q in contigs))
+    wrapped = util.write_fasta(tmp_path / "wrapped.fasta", [("c1", genome[:20000]), ("c3", genome[20010:])], width=70)
+    half = tmp_path / "half.fasta"                                        # two flat records, then a wrapped one
+    half.write_bytes(b">a\n" + genome[:15000] + b"\n>b\n" + genome[15000:30000] + b"\n>c\n" + genome[30000:40000] + b"\n" + genome[40000:] + b"\n")
+    rng = np.random.default_rng(9)
+    sr = [genome[s:s + 150] for s in rng.integers(0, len(genome) - 150, size=4000)]
+    s1 = tmp_path / "s1.fastq"
+    s1.write_bytes(fastq_text([(b"p%d/1" % i, q, b"I" * 150) for i, q in enumerate(sr[:2000])]))
+    s2 = tmp_path / "s2.fastq.gz"
+    s2.write_bytes(gzip.compress(fastq_text([(b"p%d/2" % i, q, b"I" * 150) for i, q in enumerate(sr[2000:])])))
+    cases = [
+        (["-a", str(flat), "-p", "80", "--trim", "--split", "100", str(fq)], ["device text"]),
+        (["-a", wrapped, "-p", "80", str(fq)], ["host reader"]),
+        (["-a", str(half), "-p", "80", "--trim", str(fq)], ["host reader from byte"]),
+        (["-1", str(s1), "-2", str(s2), "-p", "75", "--trim", "--split", "50", str(fq)], ["device text", "device text"]),
+    ]
+    tail = lambda e: [l.split("\r")[-1] for l in e.splitlines() if l.strip() and "[timing]" not in l and "bp)" not in l]
+    for args, how in cases:
+        rc_r, out_r, err_r = run([orc.REFCLI] + args)
+        rc_o, out_o, err_o = run([CLI] + args, {"FL_CLI_TIMING": "1", "FL_CHUNK_MB": "1"})
+        assert rc_o == rc_r == 0, err_o[-2000:]
+        notes = [l for l in err_o.splitlines() if l.startswith("[timing] reference ")]
+        assert len(notes) == len(how) and all(h in n for h, n in zip(how, notes)), notes
+        assert out_o == out_r and len(out_r) > 0
+        assert tail(err_o) == tail(err_r)
+        # the "N contigs / reads, M 16-mers" lines in full
+        count = lambda e: [l for l in e.splitlines() if "16-mers" in l and "Hashing" not in l]
+        assert count(err_o) == count(err_r)
 
 
 def test_cli_sharded_over_gpus_prints_what_one_gpu_prints(tmp_path):

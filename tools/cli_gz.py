@@ -90,6 +90,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gbp", type=float, default=1.0)
     ap.add_argument("--tmp", default=None)
+    ap.add_argument("--short-reads", type=int, default=1000000, help="reads per -1/-2 file (0: skip the reference-file case)")
     a = ap.parse_args()
     res = {"what": "filtlong CLI on gzip input: one inflate into memory + device parse against the streaming host reader"}
     with tempfile.TemporaryDirectory(prefix="flgz_", dir=a.tmp) as td:
@@ -113,6 +114,45 @@ def main():
             res[tag] = r
             os.unlink(out)
         res["all_outputs_identical"] = len(md5) == 1
+        # ---- the -1/-2 reference files: device text (fl_kmers_add_text) against the host reader ----
+        if a.short_reads > 0:
+            import numpy as np
+            rng = np.random.default_rng(5)
+            genome = cli_e2e.ACGT[rng.integers(0, 4, size=10_000_000, dtype=np.uint8)]
+            windows = np.lib.stride_tricks.sliding_window_view(genome, 150)
+            stride = max(1, len(windows) // max(a.short_reads, 1))
+            paths = []
+            for mate in (1, 2):
+                sp = os.path.join(td, "short_%d.fastq" % mate)
+                with open(sp, "wb", buffering=1 << 24) as f:
+                    for lo in range(0, a.short_reads, 200000):      # fixed-width records "@p0000000/1", filled column-wise
+                        n = min(200000, a.short_reads - lo)
+                        idx = np.arange(lo, lo + n)
+                        rec = np.empty((n, 12 + 150 + 3 + 150 + 1), dtype=np.uint8)
+                        rec[:, 0:2] = np.frombuffer(b"@p", np.uint8)
+                        for d in range(7):
+                            rec[:, 2 + d] = 48 + (idx // 10 ** (6 - d)) % 10
+                        rec[:, 9] = ord("/")
+                        rec[:, 10] = 48 + mate
+                        rec[:, 11] = 10
+                        rec[:, 12:162] = windows[(idx * stride + mate) % len(windows)]       # overlapping windows: every 16-mer many times
+                        rec[:, 162:165] = np.frombuffer(b"\n+\n", np.uint8)
+                        rec[:, 165:315] = ord("I")
+                        rec[:, 315] = 10
+                        f.write(rec.tobytes())
+                paths.append(sp)
+            small = os.path.join(td, "few.fastq")
+            cli_e2e.write_random_fastq(small, 2e7, 3, fast=True)
+            args = ["-1", paths[0], "-2", paths[1], "-p", "90", small]
+            ref = {"short_reads_per_file": a.short_reads, "bytes_per_file": os.path.getsize(paths[0])}
+            m = set()
+            for tag, env in (("device_text", {}), ("host_reader", {"FL_HOST_PARSER": "1"})):
+                out = os.path.join(td, "ref_" + tag + ".out")
+                r = run(args, env, out)
+                m.add(r.get("md5"))
+                ref[tag] = r
+            ref["outputs_identical"] = len(m) == 1
+            res["reference_files"] = ref
     print(json.dumps(res))
 
 
