@@ -114,15 +114,19 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
             int status = FL_TEXT_OK;
             check(c, fl_kmers_add_text(c, f.base + ch.begin, ch.end - ch.begin, f.format(), i + 1 == plan.size() ? 1 : 0, multi ? 1 : 0,
                                        &n_rec, &n_bases, &used, &status), "fl_kmers_add_text");
-            if (status != FL_TEXT_OK || used != ch.end - ch.begin) {    // nothing of this chunk was added: the host reader takes over here
-                if (timing) std::cerr << "[timing] reference " << filename << ": host reader from byte " << ch.begin << "\n";
-                FastxReader in(f.base + ch.begin, f.size - ch.begin);
+            if (status == FL_TEXT_OK) {                                 // the chunk's whole records (all of it, normally) are in
+                sequence_count += (int)n_rec;
+                base_count += (long long)n_bases;
+                progress(false);
+            } else {
+                used = 0;                                               // not the layout: nothing of this chunk was added
+            }
+            if (used != ch.end - ch.begin) {                            // the host reader takes over at the first byte not consumed
+                if (timing) std::cerr << "[timing] reference " << filename << ": host reader from byte " << ch.begin + used << "\n";
+                FastxReader in(f.base + ch.begin + used, f.size - ch.begin - used);
                 host_parse(in);
                 break;
             }
-            sequence_count += (int)n_rec;
-            base_count += (long long)n_bases;
-            progress(false);
             if (timing && i + 1 == plan.size()) std::cerr << "[timing] reference " << filename << ": device text, " << plan.size() << " chunks\n";
         }
     } else {
