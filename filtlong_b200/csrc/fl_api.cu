@@ -65,6 +65,7 @@ extern "C" int fl_ctx_create(const fl_params *params, int device, fl_ctx **out) 
     if (const char *f = getenv("FL_FILTER")) c->filter_enabled = atoi(f);
     if (const char *f = getenv("FL_ANCHOR")) c->anchor_enabled = atoi(f);
     if (const char *f = getenv("FL_PHRED_MODE")) c->phred_mode = atoi(f);
+    if (const char *f = getenv("FL_FASTA_TWO_LINE")) c->fasta_two_line_only = atoi(f) != 0;
     if (const char *f = getenv("FL_PHRED_OCC")) c->phred_occupancy = atoi(f);
     if (const char *f = getenv("FL_FILTER_LOG2_WORDS")) c->filter_log2_words = (unsigned)atoi(f);
     if (const char *f = getenv("FL_FILTER_KIND")) c->filter_kind_request = atoi(f);

@@ -154,6 +154,7 @@ struct fl_ctx {
     unsigned long long tie_many = 0;        // bit e: more than one table value ties there
     unsigned char tie_char[64] = {0};       // the one that does, when exactly one
     unsigned long long tie_binades_a = 0;   // bit e: some window-table value ties when w is in [2^-e, 2^(1-e))
+    bool fasta_two_line_only = false;       // fl_kmers_add_text: FASTA records of one sequence line only, no wrapped ones (FL_FASTA_TWO_LINE)
     int phred_mode = 1;                     // 1: k_phred_sum + k_phred_win (default); 0: work-item kernels (FL_PHRED_MODE)
     int phred_occupancy = 0;                // blocks per SM launched for the Phred kernels, 0 = the kernel's own default (FL_PHRED_OCC)
     int lut_window = -1;

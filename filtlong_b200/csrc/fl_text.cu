@@ -206,6 +206,127 @@ __global__ void k_text_sum_len(const int32_t *len, uint32_t n, unsigned long lon
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+// ---------------------------------------------------------------------------------------------
+// FASTA reference files whose sequences are WRAPPED (kmers.cpp:75-134 reads them through kseq, which joins the lines of
+// a record: kseq.h:199-203). A record is a '>' line and every line up to the next '>' line; when all of its sequence
+// lines but the last have one width w (and the last is not longer) -- how every assembler and `fold` write them -- base p
+// of the record is byte  first + p + p / w  of the text: no line of it has to be looked at again. Anything else (blank
+// lines, CR LF, ragged lines, a line starting with '@' or '+', which kseq takes for the next record / the quality
+// separator) is left to the host reader.
+// ---------------------------------------------------------------------------------------------
+struct FaArgs {
+    const uint8_t *text;
+    unsigned long long n_bytes;
+    const uint32_t *nl;               // newline positions
+    unsigned long long n_lines;       // real newlines
+    unsigned long long NL;            // lines, counting a last one without newline
+    unsigned long long *head;         // [NL] 1 on header lines; after the exclusive scan: headers before the line
+    uint32_t *head_line;              // [n_rec] line index of every header
+    uint32_t n_rec;
+    uint32_t *seq_off, *width;        // per record: first sequence byte, line width
+    int32_t *len;
+    unsigned long long *padded;
+    int *bad;
+};
+
+__device__ __forceinline__ unsigned long long fa_start(const FaArgs &a, unsigned long long i) { return i ? (unsigned long long)a.nl[i - 1] + 1 : 0ull; }
+__device__ __forceinline__ unsigned long long fa_end(const FaArgs &a, unsigned long long i) { return i < a.n_lines ? (unsigned long long)a.nl[i] : a.n_bytes; }
+
+// per line: header or not, and the per-line part of the validation
+__global__ void __launch_bounds__(256) k_fa_heads(FaArgs a) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.NL) return;
+    const unsigned long long s = fa_start(a, i), e = fa_end(a, i);
+    const bool h = e > s && a.text[s] == '>';
+    a.head[i] = h ? 1ull : 0ull;
+    bool bad = false;
+    if (i == 0 && !h) bad = true;                                   // the chunk must start a record
+    if (e == s) bad = true;                                         // blank line (kseq skips it; the arithmetic cannot)
+    else {
+        if (a.text[e - 1] == '\r') bad = true;                      // CR LF
+        if (!h && (a.text[s] == '@' || a.text[s] == '+')) bad = true;   // kseq.h:199: ends the sequence
+    }
+    if (bad) atomicOr(a.bad, 1);
+}
+
+// after the scan: where every header sits
+__global__ void __launch_bounds__(256) k_fa_scatter(FaArgs a) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.NL) return;
+    const unsigned long long s = fa_start(a, i), e = fa_end(a, i);
+    if (e > s && a.text[s] == '>') a.head_line[a.head[i]] = (uint32_t)i;
+}
+
+// per record: extent, width, length
+__global__ void __launch_bounds__(256) k_fa_records(FaArgs a) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n_rec) return;
+    const unsigned long long h = a.head_line[r], nxt = r + 1 < a.n_rec ? (unsigned long long)a.head_line[r + 1] : a.NL;
+    const unsigned long long k = nxt - h - 1;                       // sequence lines
+    unsigned long long so = 0, w = 1, L = 0;
+    if (k) {
+        so = fa_start(a, h + 1);
+        w = fa_end(a, h + 1) - so;
+        const unsigned long long last = fa_end(a, nxt - 1) - fa_start(a, nxt - 1);
+        L = (k - 1) * w + last;
+        if (last > w || w == 0) { atomicOr(a.bad, 1); w = 1; }
+    }
+    if (L > 0x7FFFFFFFull) { atomicOr(a.bad, 1); L = 0; }           // kseq's int length
+    a.seq_off[r] = (uint32_t)so;
+    a.width[r] = (uint32_t)w;
+    a.len[r] = (int32_t)L;
+    a.padded[r] = (L + FL_ALIGN_BASES - 1) & ~(unsigned long long)(FL_ALIGN_BASES - 1);
+}
+
+// per sequence line that is not its record's last: it must have the record's width
+__global__ void __launch_bounds__(256) k_fa_lines(FaArgs a) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.NL || i + 1 >= a.NL) return;                         // the chunk's last line is some record's last
+    const unsigned long long s = fa_start(a, i), e = fa_end(a, i);
+    if (e > s && a.text[s] == '>') return;                          // header
+    const unsigned long long s2 = e + 1, e2 = fa_end(a, i + 1);
+    if (e2 > s2 && a.text[s2] == '>') return;                       // the next line is a header: this one is its record's last
+    const unsigned long long hb = a.head[i];                        // headers before this line (>= 1 unless the chunk is bad)
+    if (hb == 0) return;
+    const unsigned long long h = a.head_line[hb - 1];
+    const unsigned long long w = fa_end(a, h + 1) - fa_start(a, h + 1);
+    if (e - s != w) atomicOr(a.bad, 1);
+}
+
+// one warp per record: 32 bases per lane and iteration, packed to 2 bits with the non-ACGT mask
+__global__ void __launch_bounds__(256) k_fa_gather(const uint8_t *__restrict__ text, uint32_t n_rec, const uint32_t *__restrict__ seq_off,
+                                                   const uint32_t *__restrict__ width, const int32_t *__restrict__ len,
+                                                   const unsigned long long *__restrict__ off, uint32_t *__restrict__ seq2b,
+                                                   uint32_t *__restrict__ nmask) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t r = warp; r < n_rec; r += n_warps) {
+        const int L = len[r];
+        const unsigned w = width[r];
+        const unsigned long long so = seq_off[r], dof = off[r];
+        const int padded = (int)(((unsigned)L + 63u) & ~63u);
+        for (int b = 32 * (int)lane; b < padded; b += 1024) {
+            unsigned q = (unsigned)b / w, col = (unsigned)b - q * w;
+            unsigned long long p = so + (unsigned)b + q;                  // byte of base b: one newline per full line before it
+            uint32_t w0 = 0, w1 = 0, m = 0;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                if (b + i < L) {
+                    const unsigned ch = text[p] & 0xDFu;                  // kmers.cpp:176-196: case folded, anything but ACGT is code 0
+                    const unsigned code = ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u;
+                    if (code == 0u && ch != 'A') m |= 1u << i;
+                    if (i < 16) w0 |= code << (30 - 2 * i);
+                    else w1 |= code << (30 - 2 * (i - 16));
+                    ++p;
+                    if (++col == w) { col = 0; ++p; }                     // step over the newline
+                }
+            }
+            reinterpret_cast<uint2 *>(seq2b + ((dof + b) >> 4))[0] = make_uint2(w0, w1);
+            nmask[(dof + b) >> 5] = m;
+        }
+    }
+}
+
 }  // namespace
 
 // The front half of both text entry points: stage the chunk, index its newlines, validate the records of the common
@@ -215,16 +336,24 @@ struct TextIndex {
     RecArgs ra{};
     const uint8_t *text = nullptr;
     unsigned long long n_rec = 0, padded_bases = 0, consumed = 0;
+    const uint32_t *fa_width = nullptr;        // wrapped-FASTA index: the records' line widths (then k_fa_gather does the packing)
     bool done = false;
 };
 
-static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lpr, int is_last_chunk, bool have_cap, uint64_t cap,
-                      uint64_t *n_records, int *status, TextIndex &ix) {
-    // ---- stage the text: copy stream, double buffered like fl_reads_push ----
+// stage the chunk (copy stream, double buffered like fl_reads_push) and count its lines
+struct TextLines {
+    fl_ctx::Staging *S = nullptr;
+    const uint8_t *text = nullptr;
+    unsigned long long n_blocks = 0, n_lines = 0, n_lines_virtual = 0;
+    unsigned grid = 0;
+    bool ends_with_nl = false;
+};
+
+static int text_lines(fl_ctx *c, const char *host_text, uint64_t n_bytes, int is_last_chunk, TextLines &tl) {
     const int slot = c->stg_next;
     c->stg_next ^= 1;
     fl_ctx::Staging &S = c->stg[slot];
-    ix.S = &S;
+    tl.S = &S;
     if (!S.consumed) FL_CUDA(c, cudaEventCreateWithFlags(&S.consumed, cudaEventDisableTiming));
     if (S.in_use) FL_CUDA(c, cudaEventSynchronize(S.consumed));
     S.in_use = false;
@@ -234,21 +363,50 @@ static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lp
     FL_CUDA(c, cudaEventRecord(c->ev_copied, c->copy_stream));
     FL_CUDA(c, cudaStreamWaitEvent(st, c->ev_copied, 0));
     const uint8_t *text = S.ascii.p;
-    ix.text = text;
-    // ---- newline index ----
-    const unsigned long long n_blocks = (n_bytes + TX_LINES_PER_WARP - 1) / TX_LINES_PER_WARP;
-    FL_CUDA(c, c->sc_u64a.reserve(n_blocks + 1, 0, st));
-    unsigned grid = fl_blocks(n_blocks * 32, 256);
-    if (grid > (unsigned)c->sm_count * 16) grid = (unsigned)c->sm_count * 16;
-    k_text_count<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p);
+    tl.text = text;
+    // ---- newline index, pass A ----
+    tl.n_blocks = (n_bytes + TX_LINES_PER_WARP - 1) / TX_LINES_PER_WARP;
+    FL_CUDA(c, c->sc_u64a.reserve(tl.n_blocks + 1, 0, st));
+    tl.grid = fl_blocks(tl.n_blocks * 32, 256);
+    if (tl.grid > (unsigned)c->sm_count * 16) tl.grid = (unsigned)c->sm_count * 16;
+    k_text_count<<<tl.grid, 256, 0, st>>>(text, n_bytes, tl.n_blocks, c->sc_u64a.p);
     c->launches++;
-    FL_TRY(fl_exclusive_scan_u64(c, c->sc_u64a.p, c->sc_u64a.p, n_blocks, c->d_scalars));
+    FL_TRY(fl_exclusive_scan_u64(c, c->sc_u64a.p, c->sc_u64a.p, tl.n_blocks, c->d_scalars));
     FL_CUDA(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 1, text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st));
     FL_CUDA(c, cudaStreamSynchronize(st));
-    unsigned long long n_lines = c->h_scalars[0];
-    const bool ends_with_nl = (reinterpret_cast<const unsigned char *>(c->h_scalars + 1))[0] == '\n';
-    unsigned long long n_lines_virtual = n_lines + ((is_last_chunk && !ends_with_nl) ? 1 : 0);   // the file's last line may lack its newline
+    tl.n_lines = c->h_scalars[0];
+    tl.ends_with_nl = (reinterpret_cast<const unsigned char *>(c->h_scalars + 1))[0] == '\n';
+    tl.n_lines_virtual = tl.n_lines + ((is_last_chunk && !tl.ends_with_nl) ? 1 : 0);   // the file's last line may lack its newline
+    return FL_OK;
+}
+
+// pass B of the newline index: positions, in order, into c->tx_nl
+static int text_positions(fl_ctx *c, uint64_t n_bytes, const TextLines &tl) {
+    FL_CUDA(c, c->tx_nl.reserve(tl.n_lines + 1, 0, c->stream));
+    k_text_positions<<<tl.grid, 256, 0, c->stream>>>(tl.text, n_bytes, tl.n_blocks, c->sc_u64a.p, c->tx_nl.p);
+    c->launches++;
+    return FL_OK;
+}
+
+static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lpr, int is_last_chunk, bool have_cap, uint64_t cap,
+                      uint64_t *n_records, int *status, TextIndex &ix) {
+    TextLines tl;
+    FL_TRY(text_lines(c, host_text, n_bytes, is_last_chunk, tl));
+    fl_ctx::Staging &S = *tl.S;
+    ix.S = &S;
+    cudaStream_t st = c->stream;
+    const uint8_t *text = tl.text;
+    ix.text = text;
+    const unsigned long long n_lines = tl.n_lines, n_lines_virtual = tl.n_lines_virtual;
+    if (lpr == 2 && (n_lines_virtual & 1ull)) {
+        // FASTA: a line left over after the last pair may continue that record's sequence (a wrapped record): the
+        // record is not what it seems, and kseq would read on. Not the simple layout.
+        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        *status = FL_TEXT_FALLBACK;
+        ix.done = true;
+        return FL_OK;
+    }
     const unsigned long long n_rec = n_lines_virtual / lpr;
     ix.n_rec = n_rec;
     if (n_rec == 0 || n_rec > 0xFFFFFFF0ull) {
@@ -264,9 +422,7 @@ static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lp
         c->set_error("fl_reads_push_text: the record arrays are too small");
         return FL_ERANGE;
     }
-    FL_CUDA(c, c->tx_nl.reserve(n_lines + 1, 0, st));
-    k_text_positions<<<grid, 256, 0, st>>>(text, n_bytes, n_blocks, c->sc_u64a.p, c->tx_nl.p);
-    c->launches++;
+    FL_TRY(text_positions(c, n_bytes, tl));
     // ---- records ----
     const size_t n = (size_t)n_rec;
     FL_CUDA(c, c->tx_u32.reserve(5 * n + 8, 0, st));
@@ -298,6 +454,65 @@ static int text_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int lp
     }
     ix.padded_bases = c->h_scalars[3];
     ix.consumed = (n_rec * lpr - 1 < n_lines) ? (unsigned long long)(*reinterpret_cast<uint32_t *>(c->h_scalars + 4)) + 1 : n_bytes;
+    return FL_OK;
+}
+
+// The index of a FASTA reference chunk whose records may be wrapped (see k_fa_heads ...): same outputs as text_index
+// (S.len, S.off, ix.ra.seq_off) plus the records' line widths. The whole chunk is consumed or nothing is.
+static int fasta_index(fl_ctx *c, const char *host_text, uint64_t n_bytes, int is_last_chunk, int *status, TextIndex &ix) {
+    TextLines tl;
+    FL_TRY(text_lines(c, host_text, n_bytes, is_last_chunk, tl));
+    fl_ctx::Staging &S = *tl.S;
+    ix.S = &S;
+    ix.text = tl.text;
+    cudaStream_t st = c->stream;
+    auto fallback = [&]() -> int {
+        FL_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        *status = FL_TEXT_FALLBACK;
+        ix.done = true;
+        return FL_OK;
+    };
+    const unsigned long long NL = tl.n_lines_virtual;
+    // a chunk that is not the file's last must end with a newline (the caller cuts at record starts), and there must be lines
+    if (NL == 0 || NL > 0xFFFFFFF0ull || (!tl.ends_with_nl && !is_last_chunk)) return fallback();
+    FL_TRY(text_positions(c, n_bytes, tl));
+    FL_CUDA(c, c->sc_u64c.reserve((size_t)NL + 1, 0, st));
+    FaArgs a{};
+    a.text = tl.text; a.n_bytes = n_bytes; a.nl = c->tx_nl.p; a.n_lines = tl.n_lines; a.NL = NL; a.head = c->sc_u64c.p;
+    int *d_bad = reinterpret_cast<int *>(c->d_scalars + 27);
+    FL_CUDA(c, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
+    a.bad = d_bad;
+    const unsigned lgrid = fl_blocks((size_t)NL, 256);
+    k_fa_heads<<<lgrid, 256, 0, st>>>(a);
+    c->launches++;
+    FL_TRY(fl_exclusive_scan_u64(c, c->sc_u64c.p, c->sc_u64c.p, (size_t)NL, c->d_scalars + 1));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 2, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 3, c->d_scalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaStreamSynchronize(st));
+    const unsigned long long n_rec = c->h_scalars[3];
+    if (c->h_scalars[2] != 0 || n_rec == 0 || n_rec > 0xFFFFFFF0ull) return fallback();
+    const size_t n = (size_t)n_rec;
+    ix.n_rec = n_rec;
+    FL_CUDA(c, c->tx_u32.reserve(3 * n + 8, 0, st));
+    FL_CUDA(c, S.off.reserve(n + 1, 0, st));
+    FL_CUDA(c, S.len.reserve(n, 0, st));
+    a.n_rec = (uint32_t)n_rec;
+    a.head_line = c->tx_u32.p; a.seq_off = c->tx_u32.p + n; a.width = c->tx_u32.p + 2 * n;
+    a.len = S.len.p; a.padded = reinterpret_cast<unsigned long long *>(S.off.p);
+    k_fa_scatter<<<lgrid, 256, 0, st>>>(a);
+    k_fa_records<<<fl_blocks(n, 256), 256, 0, st>>>(a);
+    k_fa_lines<<<lgrid, 256, 0, st>>>(a);
+    c->launches += 3;
+    FL_TRY(fl_exclusive_scan_u64(c, reinterpret_cast<unsigned long long *>(S.off.p), reinterpret_cast<unsigned long long *>(S.off.p), n, c->d_scalars + 1));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 2, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaMemcpyAsync(c->h_scalars + 3, c->d_scalars + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    FL_CUDA(c, cudaStreamSynchronize(st));
+    if (c->h_scalars[2] != 0) return fallback();
+    ix.padded_bases = c->h_scalars[3];
+    ix.consumed = n_bytes;
+    ix.ra = RecArgs{};
+    ix.ra.seq_off = a.seq_off;
+    ix.fa_width = a.width;
     return FL_OK;
 }
 
@@ -395,9 +610,9 @@ extern "C" int fl_kmers_add_text(fl_ctx *c, const char *host_text, uint64_t n_by
     *bytes_consumed = 0;
     *status = FL_TEXT_OK;
     if (n_bytes == 0) return FL_OK;
-    const int lpr = format == FL_TEXT_FASTQ ? 4 : 2;
     TextIndex ix;
-    FL_TRY(text_index(c, host_text, n_bytes, lpr, is_last_chunk, false, 0, n_records, status, ix));
+    if (format == FL_TEXT_FASTA && !c->fasta_two_line_only) FL_TRY(fasta_index(c, host_text, n_bytes, is_last_chunk, status, ix));
+    else FL_TRY(text_index(c, host_text, n_bytes, format == FL_TEXT_FASTQ ? 4 : 2, is_last_chunk, false, 0, n_records, status, ix));
     if (ix.done) return FL_OK;
     fl_ctx::Staging &S = *ix.S;
     cudaStream_t st = c->stream;
@@ -408,8 +623,12 @@ extern "C" int fl_kmers_add_text(fl_ctx *c, const char *host_text, uint64_t n_by
     if (ggrid > (unsigned)c->sm_count * 16) ggrid = (unsigned)c->sm_count * 16;
     FL_CUDA(c, S.seq.reserve((size_t)(ix.padded_bases >> 4) + 8, 0, st));
     FL_CUDA(c, S.nmask.reserve((size_t)(ix.padded_bases >> 5) + 8, 0, st));
-    k_text_gather<false><<<ggrid, 256, 0, st>>>(ix.text, n_bytes, (uint32_t)ix.n_rec, ix.ra.seq_off, S.len.p,
-                                                reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, nullptr, S.nmask.p);
+    if (ix.fa_width)
+        k_fa_gather<<<ggrid, 256, 0, st>>>(ix.text, (uint32_t)ix.n_rec, ix.ra.seq_off, ix.fa_width, S.len.p,
+                                           reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, S.nmask.p);
+    else
+        k_text_gather<false><<<ggrid, 256, 0, st>>>(ix.text, n_bytes, (uint32_t)ix.n_rec, ix.ra.seq_off, S.len.p,
+                                                    reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, nullptr, S.nmask.p);
     c->launches++;
     v.seq2b = S.seq.p;
     v.nmask = S.nmask.p;

@@ -63,8 +63,9 @@ void Kmers::add_assembly_fasta(std::string filename) {
 
 // The reference's loop (kmers.cpp:75-134) parses one record at a time through kseq on the calling thread. Here the file
 // is one byte range (mapped, or a gzip file inflated once: textsrc.h) whose record-aligned chunks go to the device as
-// TEXT (fl_kmers_add_text): records, validation, 2-bit packing and the non-ACGT mask all happen there. The first chunk
-// that is not in the common layout (wrapped FASTA, CR LF, a broken record ...) -- and everything after it -- is parsed
+// TEXT (fl_kmers_add_text): records (4-line FASTQ; FASTA with one sequence line or evenly wrapped), validation, 2-bit
+// packing and the non-ACGT mask all happen there. The first chunk that is not in that layout (CR LF, ragged or blank
+// lines, a broken record ...) -- and everything after it -- is parsed
 // by the kseq-compatible host reader from that chunk's first byte, so the adds stay in file order and the reader stops
 // where the reference's would (a parse error silently ends hashing: kmers.cpp:90-94).
 int Kmers::add_reference(const std::string &filename, bool multi) {
@@ -100,12 +101,15 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
     MappedFile f;
     std::vector<Chunk> plan;
     const bool timing = getenv("FL_CLI_TIMING") != nullptr;
-    uint64_t target = 128ull << 20;
-    if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
-    if (target < (1ull << 20)) target = 1ull << 20;
-    if (target > (1024ull << 20)) target = 1024ull << 20;
-    bool text_path = !getenv("FL_HOST_PARSER") && f.open_any(filename) && f.format() != 0 &&
-                     plan_chunks(f.base, f.size, f.format(), target, target, plan) && !plan.empty();
+    bool text_path = !getenv("FL_HOST_PARSER") && f.open_any(filename) && f.format() != 0;
+    if (text_path) {
+        // a chunk holds whole records: FASTA chunks are large enough for a chromosome on one line or wrapped
+        uint64_t target = f.format() == FL_TEXT_FASTA ? 512ull << 20 : 128ull << 20;
+        if (const char *e = getenv("FL_CHUNK_MB")) target = (uint64_t)atoll(e) << 20;
+        if (target < (1ull << 20)) target = 1ull << 20;
+        if (target > (1024ull << 20)) target = 1024ull << 20;
+        text_path = plan_chunks(f.base, f.size, f.format(), target, target, plan) && !plan.empty();
+    }
     if (text_path) {
         fl_ctx *c = context();
         for (size_t i = 0; i < plan.size(); ++i) {
@@ -122,12 +126,13 @@ int Kmers::add_reference(const std::string &filename, bool multi) {
                 used = 0;                                               // not the layout: nothing of this chunk was added
             }
             if (used != ch.end - ch.begin) {                            // the host reader takes over at the first byte not consumed
-                if (timing) std::cerr << "[timing] reference " << filename << ": host reader from byte " << ch.begin + used << "\n";
+                if (timing) std::cerr << (last_progress ? "\n" : "") << "[timing] reference " << filename << ": host reader from byte " << ch.begin + used << "\n";
                 FastxReader in(f.base + ch.begin + used, f.size - ch.begin - used);
                 host_parse(in);
                 break;
             }
-            if (timing && i + 1 == plan.size()) std::cerr << "[timing] reference " << filename << ": device text, " << plan.size() << " chunks\n";
+            if (timing && i + 1 == plan.size())
+                std::cerr << (last_progress ? "\n" : "") << "[timing] reference " << filename << ": device text, " << plan.size() << " chunks\n";
         }
     } else {
         if (timing) std::cerr << "[timing] reference " << filename << ": host reader\n";

@@ -186,10 +186,13 @@ typedef struct fl_text_records {
 int fl_reads_push_text(fl_ctx *ctx, const char *host_text, uint64_t n_bytes, int format, int is_last_chunk,
                        const fl_text_records *out, uint64_t *n_records, uint64_t *bytes_consumed, int *status);
 /* The reference set from a chunk of the reference FILE (replaces the kseq_read loop of Kmers::add_reference,
- * kmers.cpp:75-134, for the common layout): same contract as fl_reads_push_text -- the chunk starts at a record boundary,
- * 4-line FASTQ / 2-line FASTA with LF line ends, FL_TEXT_FALLBACK and nothing added otherwise -- but the records'
- * sequences go to the 16-mer set like fl_kmers_add_batch(require_multiple_copies). *n_records counts every record of
- * the chunk (kmers.cpp:96), *n_bases the bases of those of at least 16 (kmers.cpp:99-101). Chunks in file order. */
+ * kmers.cpp:75-134, for the common layouts): same contract as fl_reads_push_text -- the chunk starts at a record boundary,
+ * LF line ends, FL_TEXT_FALLBACK and nothing added otherwise -- but the records' sequences go to the 16-mer set like
+ * fl_kmers_add_batch(require_multiple_copies). FASTQ: 4-line records. FASTA: a record's sequence may be WRAPPED (kseq joins
+ * the lines, kseq.h:199-203) as long as all of its lines but the last have one width and the last is not longer (what
+ * assemblers write); a FASTA chunk that is not the file's last must end with a newline and is consumed whole or not at
+ * all. *n_records counts every record of the chunk (kmers.cpp:96), *n_bases the bases of those of at least 16
+ * (kmers.cpp:99-101). Chunks in file order. */
 int fl_kmers_add_text(fl_ctx *ctx, const char *host_text, uint64_t n_bytes, int format, int is_last_chunk,
                       int require_multiple_copies, uint64_t *n_records, uint64_t *n_bases, uint64_t *bytes_consumed, int *status);
 /* Page-locked host memory for the caller's chunk ring (portable across devices); the host side of the

@@ -166,13 +166,48 @@ def test_kmers_add_text_builds_the_set_the_packed_path_builds(multi):
     assert np.array_equal(a.kmers_export(), np.sort(ok.dump()))
     # not the common layout: nothing is added, the caller parses on the host
     before = a.kmers_count()
-    wrapped = b">c\nACGTACGTACGTACGTACGT\nACGTACGTACGTACGTACGT\n"
+    ragged = b">c\nACGTACGTACGTACGTACGT\nACGTACGT\nACGTACGTACGTACGTACGT\n"         # a middle line shorter than the first
+    longer = b">c\nACGTACGTACGTACGTACGT\nACGTACGTACGTACGTACGTACGT\n"                 # the last line longer than the first
     crlf = b">c\r\nACGTACGTACGTACGTACGTACGT\r\n"
-    for bad in (wrapped, crlf, b"@r\nACGTACGTACGTACGTAAAA\n+\nIIII\n"):
+    blank = b">c\nACGTACGTACGTACGTACGT\n\nACGTACGTACGTACGTACGT\n"
+    plus = b">c\nACGTACGTACGTACGTACGT\n+CGTACGTACGTACGTACGT\n"                        # kseq takes '+' for the quality separator
+    nohead = b"ACGTACGTACGTACGTACGT\n>c\nACGTACGTACGTACGTACGT\n"
+    for bad in (ragged, longer, crlf, blank, plus, nohead, b"@r\nACGTACGTACGTACGTAAAA\n+\nIIII\n"):
         r = a.kmers_add_text(bad, fastq=bad.startswith(b"@"), is_last=True, multiple_copies=multi)
-        assert r["status"] == "fallback" and r["n"] == 0
+        assert r["status"] == "fallback" and r["n"] == 0, bad
     assert a.kmers_count() == before
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("width", [1, 7, 31, 32, 60, 64, 70, 1000])
+def test_kmers_add_text_wrapped_fasta(width):
+    """A wrapped FASTA reference (every assembler writes them so) through fl_kmers_add_text: kseq joins a record's
+    lines (kseq.h:199-203); the device maps base p to byte first + p + p / width. Against the packed path on the joined
+    sequences, for line widths below, at and above the 32-base groups of the packer, with N runs and lower case, records
+    of one line, of exactly k full lines, empty records, and a last line without newline."""
+    rng = np.random.default_rng(100 + width)
+    genome = bytearray(util.rand_seq(rng, 9000))
+    genome[1000:1100] = b"N" * 100
+    genome[2000:2300] = bytes(genome[2000:2300]).lower()
+    genome[4000:4003] = b"RYK"
+    genome = bytes(genome)
+    seqs = [genome[:3001], genome[3001:3001 + 5 * width], genome[5000:5000 + max(width // 2, 1)], b"", genome[6000:6017], genome[7000:]]
+    wrap = lambda q: b"".join(q[i:i + width] + b"\n" for i in range(0, len(q), width))
+    text = b"".join(b">contig_%d len=%d\n" % (i, len(q)) + wrap(q) for i, q in enumerate(seqs))
+    for last_newline in (True, False):
+        a, b = api.Context(api.make_params()), api.Context(api.make_params())
+        b.kmers_add([q for q in seqs if q], False)
+        t = text if last_newline else text[:-1]
+        # two chunks, cut at a record start
+        cut = t.index(b">contig_2")
+        r1 = a.kmers_add_text(t[:cut], fastq=False, is_last=False)
+        r2 = a.kmers_add_text(t[cut:], fastq=False, is_last=True)
+        assert r1["status"] == r2["status"] == "ok" and r1["consumed"] == cut and r2["consumed"] == len(t) - cut
+        assert r1["n"] + r2["n"] == len(seqs)
+        assert r1["bases"] + r2["bases"] == sum(len(q) for q in seqs if len(q) >= 16)
+        assert a.kmers_count() == b.kmers_count() > 0
+        assert np.array_equal(a.kmers_export(), b.kmers_export())
+        a.close(); b.close()
 
 
 def run(cmd, env=None):
@@ -284,9 +319,9 @@ def test_cli_gzip_input_is_inflated_once_and_parsed_on_the_device(tmp_path):
 
 
 def test_cli_reference_files_take_the_device_text_path(tmp_path):
-    """-a with an unwrapped FASTA and -1/-2 with plain and gzip FASTQ files go to the device as text (Kmers::add_reference
-    -> fl_kmers_add_text); a wrapped FASTA and a file that turns multi-line half way go (from there on) through the
-    host reader. Same stdout and the same log lines as the reference binary every time."""
+    """-a with an unwrapped or a wrapped FASTA and -1/-2 with plain and gzip FASTQ files go to the device as text
+    (Kmers::add_reference -> fl_kmers_add_text); a file with a ragged record half way goes through the host reader from
+    that chunk on. Same stdout and the same log lines as the reference binary every time."""
     import gzip
     if not (os.path.exists(CLI) and orc.have_ref()):
         pytest.skip("CLI or reference binary not built")
@@ -297,8 +332,13 @@ def test_cli_reference_files_take_the_device_text_path(tmp_path):
     flat = tmp_path / "flat.fasta"
     flat.write_bytes(b"".join(b">" + n + b"\n" + q + b"\n" for n, q in contigs))
     wrapped = util.write_fasta(tmp_path / "wrapped.fasta", [("c1", genome[:20000]), ("c3", genome[20010:])], width=70)
-    half = tmp_path / "half.fasta"                                        # two flat records, then a wrapped one
-    half.write_bytes(b">a\n" + genome[:15000] + b"\n>b\n" + genome[15000:30000] + b"\n>c\n" + genome[30000:40000] + b"\n" + genome[40000:] + b"\n")
+    # 40 wrapped records (1.3 MB: two 1 MB chunks), the 35th with a short line in the middle: the host reader takes over
+    # in the second chunk
+    wrap = lambda q, w: b"".join(q[i:i + w] + b"\n" for i in range(0, len(q), w))
+    recs = [b">rec%d\n" % i + wrap(genome[i * 100:i * 100 + 32000], 60) for i in range(40)]
+    recs[34] = b">rec34\n" + genome[:60] + b"\n" + genome[60:90] + b"\n" + genome[90:150] + b"\n"
+    half = tmp_path / "half.fasta"
+    half.write_bytes(b"".join(recs))
     rng = np.random.default_rng(9)
     sr = [genome[s:s + 150] for s in rng.integers(0, len(genome) - 150, size=4000)]
     s1 = tmp_path / "s1.fastq"
@@ -307,7 +347,7 @@ def test_cli_reference_files_take_the_device_text_path(tmp_path):
     s2.write_bytes(gzip.compress(fastq_text([(b"p%d/2" % i, q, b"I" * 150) for i, q in enumerate(sr[2000:])])))
     cases = [
         (["-a", str(flat), "-p", "80", "--trim", "--split", "100", str(fq)], ["device text"]),
-        (["-a", wrapped, "-p", "80", str(fq)], ["host reader"]),
+        (["-a", wrapped, "-p", "80", str(fq)], ["device text"]),
         (["-a", str(half), "-p", "80", "--trim", str(fq)], ["host reader from byte"]),
         (["-1", str(s1), "-2", str(s2), "-p", "75", "--trim", "--split", "50", str(fq)], ["device text", "device text"]),
     ]
@@ -316,7 +356,7 @@ def test_cli_reference_files_take_the_device_text_path(tmp_path):
         rc_r, out_r, err_r = run([orc.REFCLI] + args)
         rc_o, out_o, err_o = run([CLI] + args, {"FL_CLI_TIMING": "1", "FL_CHUNK_MB": "1"})
         assert rc_o == rc_r == 0, err_o[-2000:]
-        notes = [l for l in err_o.splitlines() if l.startswith("[timing] reference ")]
+        notes = [l for l in err_o.splitlines() if l.startswith("[timing] reference ") and (": device text" in l or ": host reader" in l)]
         assert len(notes) == len(how) and all(h in n for h, n in zip(how, notes)), notes
         assert out_o == out_r and len(out_r) > 0
         assert tail(err_o) == tail(err_r)
