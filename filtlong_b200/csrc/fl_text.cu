@@ -293,37 +293,47 @@ __global__ void __launch_bounds__(256) k_fa_lines(FaArgs a) {
     if (e - s != w) atomicOr(a.bad, 1);
 }
 
-// one warp per record: 32 bases per lane and iteration, packed to 2 bits with the non-ACGT mask
+// 32 bases per lane and step, packed to 2 bits with the non-ACGT mask. The work is the arena's 32-base groups, not the
+// records: an assembly is a handful of records of hundreds of megabases, a read file millions of short ones, and a group
+// never straddles two records (their arena extents are multiples of 64). Each lane finds its group's record by bisection
+// over the offsets.
 __global__ void __launch_bounds__(256) k_fa_gather(const uint8_t *__restrict__ text, uint32_t n_rec, const uint32_t *__restrict__ seq_off,
                                                    const uint32_t *__restrict__ width, const int32_t *__restrict__ len,
-                                                   const unsigned long long *__restrict__ off, uint32_t *__restrict__ seq2b,
-                                                   uint32_t *__restrict__ nmask) {
-    const unsigned lane = threadIdx.x & 31;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t r = warp; r < n_rec; r += n_warps) {
+                                                   const unsigned long long *__restrict__ off, unsigned long long padded_bases,
+                                                   uint32_t *__restrict__ seq2b, uint32_t *__restrict__ nmask) {
+    const unsigned long long n_groups = padded_bases >> 5;
+    for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+         g += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long pos = g << 5;                            // arena position of the group's first base
+        uint32_t lo = 0, hi = n_rec;                                      // the last record with off[r] <= pos
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (off[mid] <= pos) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t r = lo;
         const int L = len[r];
         const unsigned w = width[r];
-        const unsigned long long so = seq_off[r], dof = off[r];
-        const int padded = (int)(((unsigned)L + 63u) & ~63u);
-        for (int b = 32 * (int)lane; b < padded; b += 1024) {
-            unsigned q = (unsigned)b / w, col = (unsigned)b - q * w;
-            unsigned long long p = so + (unsigned)b + q;                  // byte of base b: one newline per full line before it
-            uint32_t w0 = 0, w1 = 0, m = 0;
+        const unsigned long long so = seq_off[r];
+        const unsigned b = (unsigned)(pos - off[r]);                      // < the record's padded length (empty records own no group)
+        const unsigned q = b / w;
+        unsigned col = b - q * w;
+        unsigned long long p = so + b + q;                                // byte of base b: one newline per full line before it
+        uint32_t w0 = 0, w1 = 0, m = 0;
 #pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                if (b + i < L) {
-                    const unsigned ch = text[p] & 0xDFu;                  // kmers.cpp:176-196: case folded, anything but ACGT is code 0
-                    const unsigned code = ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u;
-                    if (code == 0u && ch != 'A') m |= 1u << i;
-                    if (i < 16) w0 |= code << (30 - 2 * i);
-                    else w1 |= code << (30 - 2 * (i - 16));
-                    ++p;
-                    if (++col == w) { col = 0; ++p; }                     // step over the newline
-                }
+        for (int i = 0; i < 32; ++i) {
+            if ((int)b + i < L) {
+                const unsigned ch = text[p] & 0xDFu;                      // kmers.cpp:176-196: case folded, anything but ACGT is code 0
+                const unsigned code = ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u;
+                if (code == 0u && ch != 'A') m |= 1u << i;
+                if (i < 16) w0 |= code << (30 - 2 * i);
+                else w1 |= code << (30 - 2 * (i - 16));
+                ++p;
+                if (++col == w) { col = 0; ++p; }                         // step over the newline
             }
-            reinterpret_cast<uint2 *>(seq2b + ((dof + b) >> 4))[0] = make_uint2(w0, w1);
-            nmask[(dof + b) >> 5] = m;
         }
+        reinterpret_cast<uint2 *>(seq2b)[g] = make_uint2(w0, w1);
+        nmask[g] = m;
     }
 }
 
@@ -623,10 +633,13 @@ extern "C" int fl_kmers_add_text(fl_ctx *c, const char *host_text, uint64_t n_by
     if (ggrid > (unsigned)c->sm_count * 16) ggrid = (unsigned)c->sm_count * 16;
     FL_CUDA(c, S.seq.reserve((size_t)(ix.padded_bases >> 4) + 8, 0, st));
     FL_CUDA(c, S.nmask.reserve((size_t)(ix.padded_bases >> 5) + 8, 0, st));
-    if (ix.fa_width)
-        k_fa_gather<<<ggrid, 256, 0, st>>>(ix.text, (uint32_t)ix.n_rec, ix.ra.seq_off, ix.fa_width, S.len.p,
-                                           reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, S.nmask.p);
-    else
+    if (ix.fa_width) {
+        unsigned fgrid = fl_blocks((size_t)(ix.padded_bases >> 5), 256);
+        if (fgrid > (unsigned)c->sm_count * 16) fgrid = (unsigned)c->sm_count * 16;
+        if (fgrid)
+            k_fa_gather<<<fgrid, 256, 0, st>>>(ix.text, (uint32_t)ix.n_rec, ix.ra.seq_off, ix.fa_width, S.len.p,
+                                               reinterpret_cast<unsigned long long *>(S.off.p), ix.padded_bases, S.seq.p, S.nmask.p);
+    } else
         k_text_gather<false><<<ggrid, 256, 0, st>>>(ix.text, n_bytes, (uint32_t)ix.n_rec, ix.ra.seq_off, S.len.p,
                                                     reinterpret_cast<unsigned long long *>(S.off.p), S.seq.p, nullptr, S.nmask.p);
     c->launches++;
