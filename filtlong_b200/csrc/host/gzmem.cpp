@@ -150,11 +150,19 @@ bool inflate_gzip_memory(const unsigned char *d, uint64_t n, InflatedInput &out,
         }
         std::atomic<bool> ok(true);
         std::vector<std::thread> ts;
-        for (int t = 1; t < T; ++t)
-            ts.emplace_back([&, t] {
-                if (!inflate_members(d, ms, cut[(size_t)t], cut[(size_t)t + 1], out.base)) ok.store(false);
-            });
+        int started = 1;                                               // ranges [0, started) have an owner
+        for (int t = 1; t < T; ++t) {
+            try {
+                ts.emplace_back([&, t] {
+                    if (!inflate_members(d, ms, cut[(size_t)t], cut[(size_t)t + 1], out.base)) ok.store(false);
+                });
+                started = t + 1;
+            } catch (...) {                                            // no more threads to be had: this one does the rest
+                break;
+            }
+        }
         if (!inflate_members(d, ms, cut[0], cut[1], out.base)) ok.store(false);
+        if (started < T && !inflate_members(d, ms, cut[(size_t)started], cut[(size_t)T], out.base)) ok.store(false);
         for (auto &th : ts) th.join();
         if (!ok.load()) return fail("corrupt BGZF member");
         out.size = total;
